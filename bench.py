@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- GetHI hot path, Mcells/s.
+
+A step is one complete realisation through the hot path (k-space realisation, two c2r FFTs, radial
+velocity, variance, lognormal/HI transform, HEALPix shell maps) of the configuration BASELINE.json names
+for the GPU count:  1 GPU: 512^3, nside 256, 64 shells;  2/4 GPUs: 1024^3, nside 512, 150 shells;
+8 GPUs: 2048^3, nside 1024, 150 shells (override with --grid/--nside/--shells).
+
+  value : cells / device time with the run parameters already resident on the device and the maps left
+          on the device (CUDA events on the library's stream, max over ranks)
+  e2e   : the same through the reference-facing C-ABI with HOST buffers: parameter tables sent from host
+          memory and this rank's finished maps copied back into pinned host memory inside the timed region
+  roofline     : the dominant kernel timed alone, algorithmic bytes / duration vs measured HBM peak
+  cpu_baseline : the reference's own CPU code (oracle/_ref) on the host cores, bounded sample
+  --impl reference : that CPU arm alone, same metric
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {1: (512, 256, 64), 2: (1024, 512, 150), 4: (1024, 512, 150), 8: (2048, 1024, 150)}
+# algorithmic HBM bytes per cell of each stage (single-GPU FFT has no transpose pass)
+STAGE_BYTES_PER_CELL = {"kgen": 8.0, "fft": 32.0, "fft_multi": 48.0, "vel": 8.0, "sigma": 4.0, "get_HI": 16.0, "maps": 8.0}
+
+
+def load_tables(n_nu: int) -> dict:
+    f = ROOT / "tests" / "golden" / ("ref_tables_nu64.npz" if n_nu == 64 else "ref_tables_nu150.npz")
+    t = dict(np.load(f))
+    if int(t["n_nu"]) != n_nu:  # other shell counts: n+1 uniform edges over the same band, %.6f like data/nuTable.txt
+        edges = np.array([float(f"{e:.6f}") for e in np.linspace(355.0, 945.0, n_nu + 1)])
+        t["nu0_arr"], t["nuf_arr"], t["n_nu"] = edges[:-1].copy(), edges[1:].copy(), np.asarray(n_nu)
+    return t
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=fd, stderr=subprocess.DEVNULL)
+            os.close(fd)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in Path(self.path).read_text().splitlines():
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def measured_peaks() -> tuple[float, str]:
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_run(n_grid: int, n_side: int, n_nu: int, steps: int, warmup: int) -> dict:
+    """Time the reference's own create_d_and_vr_fields + get_HI + mk_T_maps (oracle/_ref, all host
+    threads); falls back to the oracle port when the prebuilt reference is absent."""
+    from oracle.binding import Oracle, Reference, write_nutable, write_param_file
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = int(os.environ["OMP_NUM_THREADS"])
+    cells = float(n_grid) ** 3
+    times = []
+    if Reference.available():
+        kind = "reference"
+        ref = Reference()
+        tmp = tempfile.mkdtemp()
+        write_nutable(f"{tmp}/nu.txt", n_nu)
+        write_param_file(f"{tmp}/p.ini", n_grid=n_grid, n_side=n_side, nutable=f"{tmp}/nu.txt",
+                         pk_file=str(ROOT / "data" / "Pk_synth.dat"), prefix=f"{tmp}/out")
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(devnull, 1)  # the reference prints its banner and timers on stdout
+        try:
+            par = ref.read_run_params(f"{tmp}/p.ini")
+            for i in range(warmup + steps):
+                t0 = time.perf_counter()
+                ref.lib.ref_create_d_and_vr_fields(par)
+                ref.lib.ref_get_HI(par)
+                ref.grid(par, "maps_HI", (n_nu, 12 * n_side * n_side))[:] = 0
+                ref.lib.ref_mk_T_maps(par)
+                if i >= warmup:
+                    times.append(time.perf_counter() - t0)
+        finally:
+            os.dup2(saved, 1)
+            os.close(devnull)
+    else:
+        kind = "port"
+        from crime_b200 import params_from_tables
+        orc = Oracle()
+        p = params_from_tables(load_tables(n_nu), n_grid=n_grid, n_side=n_side)
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            orc.run(p)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    t = float(np.mean(times))
+    return {"value": cells / t / 1e6, "unit": "Mcells/s", "cores": cores, "kind": kind, "seconds_per_step": t,
+            "sample": f"{n_grid}^3 grid, nside {n_side}, {n_nu} shells, {len(times)} step(s); FFT stage runs the oracle's "
+                      f"own C FFT (FFTW is not installed), every other stage is the reference's code"}
+
+
+def run_reference_arm(args, workload):
+    n_grid, n_side, n_nu = workload
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sg = args.cpu_grid or min(n_grid, 256)
+    steps = max(1, min(args.steps, 3))
+    r = cpu_reference_run(sg, n_side, n_nu, steps, min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "GetHI Mcells/s end-to-end", "value": r["value"], "unit": "Mcells/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * r["seconds_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 math, f32 storage",
+        "data": "synthetic",
+        "config": {"workload": f"GetHI {n_grid}^3 grid, nside={n_side}, {n_nu} shells (timed on a bounded {sg}^3 sample)",
+                   "n_grid": n_grid, "n_side": n_side, "n_nu": n_nu, "sample_n_grid": sg},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=0)
+    ap.add_argument("--nside", type=int, default=0)
+    ap.add_argument("--shells", type=int, default=0)
+    ap.add_argument("--cpu-grid", type=int, default=0, help="grid of the bounded CPU sample (default min(grid,256))")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    wl = list(WORKLOADS.get(args.gpus, WORKLOADS[1]))
+    if args.grid: wl[0] = args.grid
+    if args.nside: wl[1] = args.nside
+    if args.shells: wl[2] = args.shells
+    n_grid, n_side, n_nu = wl
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from crime_b200 import GetHI, params_from_tables
+    from crime_b200 import abi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the GetHI hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    uid = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        buf = torch.zeros(abi.GH_CUDA_UNIQUE_ID_BYTES, dtype=torch.uint8)
+        if rank == 0:
+            import ctypes as C
+            raw = C.create_string_buffer(abi.GH_CUDA_UNIQUE_ID_BYTES)
+            lib = abi.load_library()
+            if lib.gh_cuda_get_unique_id(raw):
+                raise SystemExit(lib.gh_cuda_last_error().decode())
+            buf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
+        buf = buf.to(dev)
+        dist.broadcast(buf, 0)
+        uid = bytes(buf.cpu().numpy().tobytes())
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    tables = load_tables(n_nu)
+    params = params_from_tables(tables, n_grid=n_grid, n_side=n_side, seed=1001)
+    g = GetHI(params, rank=rank, nranks=world, unique_id=uid, device=local_rank)
+    stream = torch.cuda.ExternalStream(g.stream_handle(), device=dev)
+    cells = float(n_grid) ** 3
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), wall
+
+    def step_resident():
+        g.run(to_host=False)
+
+    def step_e2e():
+        g.set_params(params)       # host -> device: the run's parameter block and tables
+        g.run(to_host=True)        # device -> host: this rank's finished maps (pinned)
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = g.kernel_launches()
+    ms_res, _ = timed(step_resident, args.steps)
+    launches = g.kernel_launches() - l0
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, wall_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop()
+    stage_ms = g.stage_times()
+
+    # dominant kernel alone: every stage once more, each bracketed by its own events
+    g.generate_k(); g.fft_fields(); g.radial_velocity(); g.sigma_dens(); g.get_HI()
+    g.zero_maps(); g.synchronize()
+    g.accumulate_maps(); g.synchronize()
+    solo = g.stage_times()
+    nz_cells = cells / world
+    bytes_per_cell = dict(STAGE_BYTES_PER_CELL)
+    if world > 1:
+        bytes_per_cell["fft"] = bytes_per_cell["fft_multi"]
+    cand = {k: solo[k] for k in ("kgen", "fft", "vel", "sigma", "get_HI", "maps") if solo.get(k, 0) > 0}
+    top = max(cand, key=cand.get)
+    peak, peak_src = measured_peaks()
+    achieved = bytes_per_cell[top] * nz_cells / (cand[top] * 1e-3) / 1e9
+    kernel_names = {"kgen": "kgen_kernel", "fft": "fft_strided_kernel x4 + fft_c2r_rows_kernel x2", "vel": "radial_velocity_kernel",
+                    "sigma": "sigma_partial_kernel", "get_HI": "get_HI_kernel", "maps": "accumulate_kernel"}
+    traffic = None
+    tf = ROOT / "profiles" / "roofline_traffic.json"
+    if tf.exists():
+        try:
+            traffic = json.loads(tf.read_text()).get(f"{top}:{n_grid}")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": kernel_names[top], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_cell": bytes_per_cell[top], "ms": cand[top],
+                "stage_ms_alone": {k: round(v, 4) for k, v in solo.items()},
+                "stage_frac_of_hbm_peak": {k: round(bytes_per_cell[k] * nz_cells / (v * 1e-3) / 1e9 / peak, 4) for k, v in cand.items()}}
+    if top == "maps":
+        n_sub = 10.0 * nz_cells
+        roofline["note"] = ("accumulate_kernel is bound by fp64 instruction and L2 atomic throughput, not HBM "
+                            "(SURVEY 8d): also reporting sub-particles/s")
+        roofline["subparticles_per_s"] = n_sub / (cand[top] * 1e-3)
+
+    n_here = g.n_shells_here
+    table_bytes = sum(np.asarray(v).nbytes for k, v in tables.items() if k in abi.TABLE_FIELDS)
+    maps_bytes = n_here * g.npix * 4
+    if world > 1:
+        mb = torch.tensor([float(maps_bytes), float(table_bytes)], device=dev, dtype=torch.float64)
+        dist.all_reduce(mb)
+        maps_bytes, table_bytes = int(mb[0].item()), int(mb[1].item())
+
+    if rank == 0:
+        line = {
+            "metric": "GetHI Mcells/s end-to-end", "value": cells * args.steps / (ms_res * 1e-3) / 1e6, "unit": "Mcells/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 fields, f64 index arithmetic",
+            "data": "synthetic",
+            "config": {"workload": f"GetHI {n_grid}^3 grid, nside={n_side}, {n_nu} shells", "n_grid": n_grid, "n_side": n_side,
+                       "n_nu": n_nu, "slabs": world, "cells_per_gpu": nz_cells,
+                       "l2": "inputs larger than L2: three %.2f GiB grids per GPU are swept every step" % (cells / world * 4 * (1 + 2.0 / n_grid) / 2**30)},
+            "e2e": {"value": cells * args.steps / (ms_e2e * 1e-3) / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": table_bytes,
+                    "d2h_bytes_per_step": maps_bytes, "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": 1e3 * wall_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "stage_ms_last_e2e_step": {k: round(v, 4) for k, v in stage_ms.items()},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            sg = args.cpu_grid or min(n_grid, 256)
+            try:
+                cb = cpu_reference_run(sg, n_side, n_nu, 1, 0)
+                line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as exc:  # the CPU arm must never take the GPU line down with it
+                line["cpu_baseline"] = {"value": None, "unit": "Mcells/s", "cores": os.cpu_count(), "kind": "port",
+                                        "sample": f"failed: {exc}"}
+        print(json.dumps(line), flush=True)
+    g.end_fftw()
+    if world > 1:
+        dist.barrier(device_ids=[local_rank])
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,621 @@
+// C-ABI of libgh_cuda.so (include/gh_cuda.h): context, memory, stage sequencing, NCCL plumbing.
+// One process per GPU; rank r owns z planes [r*N/P,(r+1)*N/P) of the real-space grids, ky rows of the
+// same range of the k-space grids, and ceil(n_nu/P) shells of the reduced map stack.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <new>
+#include "gh_internal.cuh"
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+
+void gh_set_error(const char *fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char *gh_cuda_last_error(void) { return g_err; }
+extern "C" const char *gh_cuda_version(void) { return "gh_cuda 0.1 (sm_100a)"; }
+
+#define GH_REQUIRE(cond, ...)      \
+  do {                             \
+    if (!(cond)) {                 \
+      gh_set_error(__VA_ARGS__);   \
+      return 1;                    \
+    }                              \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ MT19937
+// mk_T_maps draws its 30 sub-particle offsets from gsl_rng_mt19937 seeded with seed_rng
+// (src/pixelize.c:157-164, src/common.c:133-146).  30 draws on the host; GSL maps seed 0 to 4357 and
+// returns u32 / 2^32.
+namespace {
+struct Mt19937 {
+  uint32_t mt[624];
+  int idx;
+  explicit Mt19937(uint32_t seed)
+  {
+    if (seed == 0) seed = 4357;
+    mt[0] = seed;
+    for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+    idx = 624;
+  }
+  uint32_t next()
+  {
+    if (idx >= 624) {
+      for (int k = 0; k < 624; ++k) {
+        const uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+        mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      }
+      idx = 0;
+    }
+    uint32_t y = mt[idx++];
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+  }
+  double uniform() { return next() / 4294967296.0; }
+};
+
+// src/cosmo.c:40-50
+double host_r_of_z(const gh_cuda_params *p, double z)
+{
+  if (z <= 0) return 0;
+  if (z >= p->z_arr_z2r[p->nz_tab - 1]) return p->r_arr_z2r[p->nz_tab - 1];
+  const int iz = (int)(z / p->dz_tab);
+  return p->r_arr_z2r[iz] + (p->r_arr_z2r[iz + 1] - p->r_arr_z2r[iz]) * (z - p->z_arr_z2r[iz]) / p->dz_tab;
+}
+
+struct StageTimer {
+  gh_cuda_ctx *c;
+  int slot;
+  StageTimer(gh_cuda_ctx *ctx, int s) : c(ctx), slot(s) { cudaEventRecord(c->ev[2 * slot], c->stream); }
+  ~StageTimer()
+  {
+    cudaEventRecord(c->ev[2 * slot + 1], c->stream);
+    c->ev_used[slot] = true;
+  }
+};
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ create / destroy
+extern "C" int gh_cuda_get_unique_id(void *id_out)
+{
+  GH_REQUIRE(id_out, "gh_cuda_get_unique_id: null output");
+  static_assert(sizeof(ncclUniqueId) <= GH_CUDA_UNIQUE_ID_BYTES, "unique id size");
+  ncclUniqueId id;
+  GH_NCCL_OK(ncclGetUniqueId(&id));
+  memset(id_out, 0, GH_CUDA_UNIQUE_ID_BYTES);
+  memcpy(id_out, &id, sizeof(id));
+  return 0;
+}
+
+static int upload_tables(gh_cuda_ctx *c, const gh_cuda_params *p)
+{
+  GhDev &d = c->d;
+  const int nz = p->nz_tab, nk = p->numk, nn = p->n_nu;
+  // layout: doubles first, then floats
+  const size_t n_dbl = (size_t)2 * nk + 4 * nz + 2 * nn;
+  const size_t n_flt = (size_t)3 * nz;
+  const size_t bytes = n_dbl * sizeof(double) + n_flt * sizeof(float);
+  char *h = (char *)malloc(bytes);
+  GH_REQUIRE(h, "out of host memory");
+  double *hd = (double *)h;
+  float *hf = (float *)(h + n_dbl * sizeof(double));
+  size_t o = 0;
+  auto putd = [&](const double *src, int n) { size_t at = o; memcpy(hd + o, src, sizeof(double) * n); o += n; return at; };
+  const size_t o_logk = putd(p->logkarr, nk), o_pk = putd(p->pkarr, nk);
+  const size_t o_z = putd(p->z_arr_r2z, nz), o_r = putd(p->r_arr_r2z, nz);
+  const size_t o_gd = putd(p->growth_d_arr, nz), o_gv = putd(p->growth_v_arr, nz);
+  size_t o_nu0 = o, o_nuf = o;
+  if (p->irregular_nutable) { o_nu0 = putd(p->nu0_arr, nn); o_nuf = putd(p->nuf_arr, nn); }
+  for (int i = 0; i < nz; ++i) {
+    hf[i] = (float)p->z_arr_r2z[i];
+    hf[nz + i] = (float)p->growth_d_arr[i];
+    hf[2 * nz + i] = (float)p->growth_v_arr[i];
+  }
+  cudaError_t e = cudaSuccess;
+  if (!c->d_tables) { e = cudaMalloc(&c->d_tables, bytes); c->tables_bytes = bytes; }
+  else if (bytes != c->tables_bytes) { free(h); gh_set_error("table sizes changed; create a new context"); return 1; }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_tables, h, bytes, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  free(h);
+  GH_REQUIRE(e == cudaSuccess, "table upload failed: %s", cudaGetErrorString(e));
+  const double *dd = (const double *)c->d_tables;
+  const float *df = (const float *)((const char *)c->d_tables + n_dbl * sizeof(double));
+  d.logkarr = dd + o_logk; d.pkarr = dd + o_pk;
+  d.z_r2z = dd + o_z; d.r_r2z = dd + o_r; d.gd = dd + o_gd; d.gv = dd + o_gv;
+  d.nu0 = dd + o_nu0; d.nuf = dd + o_nuf;
+  d.z_r2z_f = df; d.gd_f = df + nz; d.gv_f = df + 2 * nz;
+  return 0;
+}
+
+// scalars, sub-particle offsets and per-shell prefactors derived from the parameter block
+static int apply_params(gh_cuda_ctx *c, const gh_cuda_params *p, int rank, int nranks)
+{
+  GhDev &d = c->d;
+  d.n = p->n_grid; d.nh = p->n_grid / 2 + 1;
+  d.nranks = nranks; d.rank = rank;
+  d.nz_here = d.n / nranks; d.iz0 = rank * d.nz_here;
+  d.nky_here = d.nz_here; d.ky0 = d.iz0;
+  d.l_box = p->l_box; d.dx = p->l_box / p->n_grid;
+  for (int i = 0; i < 3; ++i) d.pos_obs[i] = p->pos_obs[i];
+  d.seed = p->seed_rng; d.do_smoothing = p->do_smoothing; d.r2_smooth = p->r2_smooth;
+  d.vfactor = p->fgrowth_0 * p->hubble_0;
+  d.dk = 2 * M_PI / p->l_box; d.idk3 = 1. / (d.dk * d.dk * d.dk);
+  d.numk = p->numk; d.logkmin = p->logkmin; d.logkmax = p->logkmax; d.idlogk = p->idlogk; d.n_scal = p->n_scal;
+  d.nz_tab = p->nz_tab; d.glob_idr = p->glob_idr; d.r_tab_max = p->r_arr_r2z[p->nz_tab - 1];
+  d.nside = p->n_side; d.npix = 12LL * p->n_side * p->n_side;
+  d.n_nu = p->n_nu; d.irregular = p->irregular_nutable;
+  const int shells_per_rank = (p->n_nu + nranks - 1) / nranks;
+  d.n_nu_pad = shells_per_rank * nranks;
+  if (p->irregular_nutable) { d.nu_min = p->nu0_arr[0]; d.nu_max = p->nuf_arr[p->n_nu - 1]; }
+  else { d.nu_min = p->nu_min; d.nu_max = p->nu_max; }
+  d.inv_dnu = p->n_nu / (d.nu_max - d.nu_min);  // src/pixelize.c:176-178
+  {
+    // redshift window that can still land in a shell: nu in [nu_lo, nu_hi); the regular-table personality
+    // truncates toward zero, which also accepts (nu_min - dnu, nu_min) into shell 0 (src/pixelize.c:216)
+    const double nu_lo = p->irregular_nutable ? d.nu_min : d.nu_min - 1.0 / d.inv_dnu;
+    d.z_hi_cull = GH_CUDA_NU_21 / nu_lo - 1 + 1e-9;
+    d.z_lo_cull = GH_CUDA_NU_21 / d.nu_max - 1 - 1e-9;
+  }
+  {
+    Mt19937 g(p->seed_rng);
+    const double lcell = p->l_box / p->n_grid;
+    for (int i = 0; i < GH_CUDA_N_SUBPART; ++i) {  // interleaved x,y,z draws, src/pixelize.c:160-164
+      d.sub_off[i] = lcell * (g.uniform() - 0.5);
+      d.sub_off[GH_CUDA_N_SUBPART + i] = lcell * (g.uniform() - 0.5);
+      d.sub_off[2 * GH_CUDA_N_SUBPART + i] = lcell * (g.uniform() - 0.5);
+    }
+  }
+  {
+    // src/pixelize.c:155,246-256
+    const double m2t = 90.057156 * p->OmegaB * p->hhub * (double)d.npix / (4 * M_PI);
+    for (int inu = 0; inu < d.n_nu_pad; ++inu) {
+      if (inu >= p->n_nu) { c->h_prefac[inu] = 0; continue; }
+      double dnu, nu;
+      if (p->irregular_nutable) { dnu = p->nuf_arr[inu] - p->nu0_arr[inu]; nu = (p->nuf_arr[inu] + p->nu0_arr[inu]) * 0.5; }
+      else { dnu = (p->nu_max - p->nu_min) / p->n_nu; nu = p->nu_min + (inu + 0.5) * dnu; }
+      const double r = host_r_of_z(p, GH_CUDA_NU_21 / nu - 1);
+      c->h_prefac[inu] = m2t / (r * r * dnu);
+    }
+  }
+
+  return 0;
+}
+
+extern "C" int gh_cuda_destroy(gh_cuda_ctx *c)
+{
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->have_comm) ncclCommDestroy(c->comm);
+  cudaFree(c->gridA); cudaFree(c->gridB); cudaFree(c->gridC);
+  cudaFree(c->halo_lo); cudaFree(c->halo_hi);
+  cudaFree(c->maps); cudaFree(c->maps_recv);
+  cudaFree(c->twiddle); cudaFree(c->d_partials); cudaFree(c->d_prefac); cudaFree(c->d_tables);
+  for (int i = 0; i < 2 * GH_T_NSLOTS; ++i)
+    if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+extern "C" int gh_cuda_create(const gh_cuda_params *p, int rank, int nranks, const void *unique_id, int device,
+                              gh_cuda_ctx **ctx_out)
+{
+  GH_REQUIRE(p && ctx_out, "gh_cuda_create: null argument");
+  *ctx_out = nullptr;
+  GH_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "gh_cuda_create: bad rank %d of %d", rank, nranks);
+  GH_REQUIRE(gh_fft_supported(p->n_grid), "n_grid=%d unsupported (powers of two 32..4096)", p->n_grid);
+  GH_REQUIRE((nranks & (nranks - 1)) == 0 && p->n_grid % nranks == 0 && p->n_grid / nranks >= 2,
+             "n_grid=%d cannot be split into %d slabs (need a power-of-two rank count, >=2 planes each)", p->n_grid, nranks);
+  GH_REQUIRE(p->n_side >= 1 && p->n_nu >= 1 && p->n_nu <= 4096, "bad n_side=%ld / n_nu=%d", p->n_side, p->n_nu);
+  GH_REQUIRE(p->nz_tab >= 2 && p->nz_tab <= GH_NZ_TAB_MAX && p->numk >= 2, "bad table sizes");
+  GH_REQUIRE(p->logkarr && p->pkarr && p->z_arr_r2z && p->r_arr_r2z && p->growth_d_arr && p->growth_v_arr &&
+                 p->z_arr_z2r && p->r_arr_z2r, "gh_cuda_create: missing table pointer");
+  GH_REQUIRE(!p->irregular_nutable || (p->nu0_arr && p->nuf_arr), "irregular nu table requested but not supplied");
+  if (p->irregular_nutable)
+    for (int i = 0; i + 1 < p->n_nu; ++i)
+      GH_REQUIRE(p->nuf_arr[i] == p->nu0_arr[i + 1], "frequency bins must be contiguous (the reference's get_inu never terminates otherwise)");
+  GH_REQUIRE(nranks == 1 || unique_id, "gh_cuda_create: nranks>1 needs the NCCL unique id");
+
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  GH_REQUIRE(e == cudaSuccess && ndev > 0, "no CUDA device available (%s); libgh_cuda has no CPU fallback",
+             e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  GH_REQUIRE(device >= 0 && device < ndev, "device %d out of range (%d visible)", device, ndev);
+  GH_CUDA_OK(cudaSetDevice(device));
+
+  gh_cuda_ctx *c = new (std::nothrow) gh_cuda_ctx();
+  GH_REQUIRE(c, "out of host memory");
+  memset(c, 0, sizeof(*c));
+  c->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; gh_set_error("cudaGetDeviceProperties failed"); return 1; }
+  c->n_sm = prop.multiProcessorCount;
+
+  if (apply_params(c, p, rank, nranks)) { delete c; return 1; }
+  GhDev &d = c->d;
+  const int shells_per_rank = d.n_nu_pad / nranks;
+
+#define CREATE_OK(call)                                                                                   \
+  do {                                                                                                    \
+    cudaError_t e__ = (call);                                                                             \
+    if (e__ != cudaSuccess) {                                                                             \
+      gh_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));           \
+      gh_cuda_destroy(c);                                                                                 \
+      return 1;                                                                                           \
+    }                                                                                                     \
+  } while (0)
+
+  CREATE_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2 * GH_T_NSLOTS; ++i) CREATE_OK(cudaEventCreate(&c->ev[i]));
+  if (upload_tables(c, p)) { gh_cuda_destroy(c); return 1; }
+
+  c->slab_complex = (size_t)d.nz_here * d.n * d.nh;
+  const size_t slab_bytes = c->slab_complex * sizeof(float2);
+  CREATE_OK(cudaMalloc(&c->gridA, slab_bytes));
+  CREATE_OK(cudaMalloc(&c->gridB, slab_bytes));
+  CREATE_OK(cudaMalloc(&c->gridC, slab_bytes));
+  const size_t map_bytes = (size_t)d.n_nu_pad * d.npix * sizeof(float);
+  CREATE_OK(cudaMalloc(&c->maps, map_bytes));
+  CREATE_OK(cudaMemsetAsync(c->maps, 0, map_bytes, c->stream));
+  if (nranks > 1) {
+    const size_t plane_bytes = (size_t)2 * d.nh * d.n * sizeof(float);
+    CREATE_OK(cudaMalloc(&c->halo_lo, plane_bytes));
+    CREATE_OK(cudaMalloc(&c->halo_hi, plane_bytes));
+    CREATE_OK(cudaMalloc(&c->maps_recv, (size_t)shells_per_rank * d.npix * sizeof(float)));
+  }
+  CREATE_OK(cudaMalloc(&c->d_partials, sizeof(double) * (2 + 2 * (size_t)c->n_sm * 8)));
+  CREATE_OK(cudaMalloc(&c->d_prefac, sizeof(double) * d.n_nu_pad));
+  CREATE_OK(cudaMemcpyAsync(c->d_prefac, c->h_prefac, sizeof(double) * d.n_nu_pad, cudaMemcpyHostToDevice, c->stream));
+  {
+    float2 *tw = (float2 *)malloc(sizeof(float2) * d.n);
+    if (!tw) { gh_cuda_destroy(c); gh_set_error("out of host memory"); return 1; }
+    for (int j = 0; j < d.n; ++j) {
+      const double a = 2.0 * M_PI * (double)j / (double)d.n;
+      tw[j] = make_float2((float)cos(a), (float)sin(a));
+    }
+    cudaError_t e2 = cudaMalloc(&c->twiddle, sizeof(float2) * d.n);
+    if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(c->twiddle, tw, sizeof(float2) * d.n, cudaMemcpyHostToDevice, c->stream);
+    if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(c->stream);
+    free(tw);
+    CREATE_OK(e2);
+  }
+  if (nranks > 1) {
+    ncclUniqueId id;
+    memcpy(&id, unique_id, sizeof(id));
+    ncclResult_t r = ncclCommInitRank(&c->comm, nranks, id, rank);
+    if (r != ncclSuccess) {
+      gh_set_error("ncclCommInitRank failed: %s", ncclGetErrorString(r));
+      gh_cuda_destroy(c);
+      return 1;
+    }
+    c->have_comm = true;
+  }
+  CREATE_OK(cudaStreamSynchronize(c->stream));
+#undef CREATE_OK
+  c->sigma2_gauss = -1;
+  *ctx_out = c;
+  return 0;
+}
+
+extern "C" int gh_cuda_set_params(gh_cuda_ctx *c, const gh_cuda_params *p)
+{
+  GH_REQUIRE(c && p, "gh_cuda_set_params: null argument");
+  GH_CUDA_OK(cudaSetDevice(c->device));
+  GH_REQUIRE(p->n_grid == c->d.n && p->n_side == c->d.nside && p->n_nu == c->d.n_nu && p->nz_tab == c->d.nz_tab &&
+                 p->numk == c->d.numk && p->irregular_nutable == c->d.irregular,
+             "gh_cuda_set_params: grid / sky / table sizes differ from the context's; create a new context");
+  GH_REQUIRE(p->logkarr && p->pkarr && p->z_arr_r2z && p->r_arr_r2z && p->growth_d_arr && p->growth_v_arr &&
+                 p->z_arr_z2r && p->r_arr_z2r && (!p->irregular_nutable || (p->nu0_arr && p->nuf_arr)),
+             "gh_cuda_set_params: missing table pointer");
+  if (apply_params(c, p, c->d.rank, c->d.nranks)) return 1;
+  if (upload_tables(c, p)) return 1;
+  GH_CUDA_OK(cudaMemcpyAsync(c->d_prefac, c->h_prefac, sizeof(double) * c->d.n_nu_pad, cudaMemcpyHostToDevice, c->stream));
+  GH_CUDA_OK(cudaStreamSynchronize(c->stream));
+  c->sigma_overridden = false;
+  return 0;
+}
+
+#define GH_CTX(c)                                             \
+  GH_REQUIRE((c) != nullptr, "null gh_cuda context");         \
+  GH_CUDA_OK(cudaSetDevice((c)->device))
+
+extern "C" int gh_cuda_slab(const gh_cuda_ctx *c, int *nz_here, int *iz0_here)
+{
+  GH_REQUIRE(c, "null gh_cuda context");
+  if (nz_here) *nz_here = c->d.nz_here;
+  if (iz0_here) *iz0_here = c->d.iz0;
+  return 0;
+}
+
+extern "C" int gh_cuda_shells(const gh_cuda_ctx *c, int *n_shells_here, int *shell0_here)
+{
+  GH_REQUIRE(c, "null gh_cuda context");
+  const int per = c->d.n_nu_pad / c->d.nranks;
+  const int s0 = c->d.rank * per;
+  int n = c->d.n_nu - s0;
+  if (n > per) n = per;
+  if (n < 0) n = 0;
+  if (n_shells_here) *n_shells_here = n;
+  if (shell0_here) *shell0_here = s0;
+  return 0;
+}
+
+extern "C" int gh_cuda_synchronize(gh_cuda_ctx *c)
+{
+  GH_CTX(c);
+  GH_CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" void *gh_cuda_stream(const gh_cuda_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" unsigned long long gh_cuda_kernel_launches(const gh_cuda_ctx *c) { return c ? c->launches : 0ULL; }
+
+extern "C" int gh_cuda_host_alloc(void **ptr, unsigned long long bytes)
+{
+  GH_REQUIRE(ptr, "null pointer");
+  GH_CUDA_OK(cudaMallocHost(ptr, bytes));
+  return 0;
+}
+extern "C" int gh_cuda_host_free(void *ptr)
+{
+  GH_CUDA_OK(cudaFreeHost(ptr));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ stages
+extern "C" int gh_cuda_generate_k(gh_cuda_ctx *c)
+{
+  GH_CTX(c);
+  StageTimer t(c, GH_T_KGEN);
+  return gh_launch_kgen(c);
+}
+
+extern "C" int gh_cuda_fft_fields(gh_cuda_ctx *c)
+{
+  GH_CTX(c);
+  StageTimer t(c, GH_T_FFT);
+  if (gh_launch_fft_field(c, c->gridA)) return 1;  // src/fourier.c:391
+  return gh_launch_fft_field(c, c->gridB);         // src/fourier.c:392
+}
+
+extern "C" int gh_cuda_radial_velocity(gh_cuda_ctx *c)
+{
+  GH_CTX(c);
+  StageTimer t(c, GH_T_VEL);
+  return gh_launch_radial_velocity(c);
+}
+
+extern "C" int gh_cuda_sigma_dens(gh_cuda_ctx *c, double *sigma2_out, double *mean_out)
+{
+  GH_CTX(c);
+  double sums[2];
+  {
+    StageTimer t(c, GH_T_SIGMA);
+    if (gh_launch_sigma(c)) return 1;
+    if (c->d.nranks > 1) GH_NCCL_OK(ncclAllReduce(c->d_partials, c->d_partials, 2, ncclDouble, ncclSum, c->comm, c->stream));
+  }
+  GH_CUDA_OK(cudaMemcpyAsync(sums, c->d_partials, sizeof(sums), cudaMemcpyDeviceToHost, c->stream));
+  GH_CUDA_OK(cudaStreamSynchronize(c->stream));
+  const double ng_tot = (double)c->d.n * ((double)c->d.n * (double)c->d.n);
+  const double mean = sums[0] / ng_tot;  // src/fourier.c:59-60,74
+  c->mean_gauss = mean;
+  if (!c->sigma_overridden) c->sigma2_gauss = sums[1] / ng_tot - mean * mean;
+  if (sigma2_out) *sigma2_out = sums[1] / ng_tot - mean * mean;
+  if (mean_out) *mean_out = mean;
+  return 0;
+}
+
+extern "C" int gh_cuda_create_d_and_vr_fields(gh_cuda_ctx *c, double *sigma2_out, double *mean_out)
+{
+  GH_CTX(c);
+  if (!c->k_injected && gh_cuda_generate_k(c)) return 1;
+  if (gh_cuda_fft_fields(c)) return 1;
+  if (gh_cuda_radial_velocity(c)) return 1;
+  return gh_cuda_sigma_dens(c, sigma2_out, mean_out);
+}
+
+extern "C" int gh_cuda_get_HI(gh_cuda_ctx *c)
+{
+  GH_CTX(c);
+  GH_REQUIRE(c->sigma2_gauss >= 0, "gh_cuda_get_HI: sigma2_gauss not set (run create_d_and_vr_fields or set it)");
+  StageTimer t(c, GH_T_GETHI);
+  return gh_launch_get_HI(c);
+}
+
+extern "C" int gh_cuda_zero_maps(gh_cuda_ctx *c)
+{
+  GH_CTX(c);
+  GH_CUDA_OK(cudaMemsetAsync(c->maps, 0, (size_t)c->d.n_nu_pad * c->d.npix * sizeof(float), c->stream));
+  return 0;
+}
+
+extern "C" int gh_cuda_accumulate_maps(gh_cuda_ctx *c)
+{
+  GH_CTX(c);
+  StageTimer t(c, GH_T_MAPS);
+  return gh_launch_accumulate(c);
+}
+
+extern "C" int gh_cuda_mk_T_maps(gh_cuda_ctx *c, float *maps_host)
+{
+  GH_CTX(c);
+  const GhDev &d = c->d;
+  int n_here = 0, s0 = 0;
+  gh_cuda_shells(c, &n_here, &s0);
+  float *result = c->maps;
+  if (d.nranks == 1) {
+    StageTimer t(c, GH_T_MAPS);
+    if (gh_cuda_zero_maps(c)) return 1;
+    if (gh_launch_accumulate(c)) return 1;
+    if (gh_launch_scale_maps(c, c->maps, 0, d.n_nu)) return 1;
+  } else {
+    {
+      StageTimer t(c, GH_T_MAPS);
+      if (gh_cuda_zero_maps(c)) return 1;
+      if (gh_launch_accumulate(c)) return 1;
+    }
+    {
+      // the reference sums full per-rank stacks onto rank 0 (src/pixelize.c:266-284); here every rank ends
+      // up with the sum of its own shells, then scales just those
+      StageTimer t(c, GH_T_REDUCE);
+      const size_t per = (size_t)(d.n_nu_pad / d.nranks) * d.npix;
+      GH_NCCL_OK(ncclReduceScatter(c->maps, c->maps_recv, per, ncclFloat, ncclSum, c->comm, c->stream));
+      if (gh_launch_scale_maps(c, c->maps_recv, s0, n_here)) return 1;
+    }
+    result = c->maps_recv;
+  }
+  if (maps_host && n_here > 0) {
+    StageTimer t(c, GH_T_D2H);
+    GH_CUDA_OK(cudaMemcpyAsync(maps_host, result, (size_t)n_here * d.npix * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  }
+  GH_CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int gh_cuda_run(gh_cuda_ctx *c, double *sigma2_out, float *maps_host)
+{
+  if (gh_cuda_create_d_and_vr_fields(c, sigma2_out, nullptr)) return 1;
+  if (gh_cuda_get_HI(c)) return 1;
+  return gh_cuda_mk_T_maps(c, maps_host);
+}
+
+// ------------------------------------------------------------------------------------------------ injection / read-back
+static float2 *grid_ptr(gh_cuda_ctx *c, int which)
+{
+  return which == GH_GRID_DENS ? c->gridA : which == GH_GRID_VPOT ? c->gridB : which == GH_GRID_RVEL ? c->gridC : nullptr;
+}
+
+extern "C" int gh_cuda_set_delta_k(gh_cuda_ctx *c, const float *dens_k, const float *vpot_k)
+{
+  GH_CTX(c);
+  GH_REQUIRE(dens_k && vpot_k, "gh_cuda_set_delta_k: null field");
+  const GhDev &d = c->d;
+  // global [kz][ky][kx] -> local [kz][ky_local][kx]: per kz one contiguous run of nky_here*nh modes
+  const size_t width = (size_t)d.nky_here * d.nh * sizeof(float2), spitch = (size_t)d.n * d.nh * sizeof(float2);
+  const size_t off = (size_t)d.ky0 * d.nh * 2;  // floats
+  GH_CUDA_OK(cudaMemcpy2DAsync(c->gridA, width, dens_k + off, spitch, width, d.n, cudaMemcpyHostToDevice, c->stream));
+  GH_CUDA_OK(cudaMemcpy2DAsync(c->gridB, width, vpot_k + off, spitch, width, d.n, cudaMemcpyHostToDevice, c->stream));
+  GH_CUDA_OK(cudaStreamSynchronize(c->stream));
+  c->k_injected = true;
+  return 0;
+}
+
+extern "C" int gh_cuda_clear_delta_k(gh_cuda_ctx *c)
+{
+  GH_REQUIRE(c, "null gh_cuda context");
+  c->k_injected = false;
+  return 0;
+}
+
+extern "C" int gh_cuda_download_delta_k(gh_cuda_ctx *c, float *dens_k, float *vpot_k)
+{
+  GH_CTX(c);
+  const GhDev &d = c->d;
+  const size_t width = (size_t)d.nky_here * d.nh * sizeof(float2), dpitch = (size_t)d.n * d.nh * sizeof(float2);
+  const size_t off = (size_t)d.ky0 * d.nh * 2;
+  if (dens_k) GH_CUDA_OK(cudaMemcpy2DAsync(dens_k + off, dpitch, c->gridA, width, width, d.n, cudaMemcpyDeviceToHost, c->stream));
+  if (vpot_k) GH_CUDA_OK(cudaMemcpy2DAsync(vpot_k + off, dpitch, c->gridB, width, width, d.n, cudaMemcpyDeviceToHost, c->stream));
+  GH_CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int gh_cuda_download_grid(gh_cuda_ctx *c, int which, float *slab_out)
+{
+  GH_CTX(c);
+  float2 *g = grid_ptr(c, which);
+  GH_REQUIRE(g && slab_out, "gh_cuda_download_grid: bad grid id %d or null output", which);
+  GH_CUDA_OK(cudaMemcpyAsync(slab_out, g, c->slab_complex * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+  GH_CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int gh_cuda_upload_grid(gh_cuda_ctx *c, int which, const float *slab_in)
+{
+  GH_CTX(c);
+  float2 *g = grid_ptr(c, which);
+  GH_REQUIRE(g && slab_in, "gh_cuda_upload_grid: bad grid id %d or null input", which);
+  GH_CUDA_OK(cudaMemcpyAsync(g, slab_in, c->slab_complex * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+  GH_CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int gh_cuda_set_sigma2_gauss(gh_cuda_ctx *c, double sigma2)
+{
+  GH_REQUIRE(c, "null gh_cuda context");
+  c->sigma2_gauss = sigma2;
+  c->sigma_overridden = true;
+  return 0;
+}
+
+extern "C" int gh_cuda_download_maps(gh_cuda_ctx *c, float *maps_out, unsigned long long first, unsigned long long n_floats)
+{
+  GH_CTX(c);
+  const unsigned long long total = (unsigned long long)c->d.n_nu_pad * c->d.npix;
+  GH_REQUIRE(maps_out && first + n_floats <= total, "gh_cuda_download_maps: range out of bounds");
+  GH_CUDA_OK(cudaMemcpyAsync(maps_out, c->maps + first, n_floats * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  GH_CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int gh_cuda_subparticle_offsets(const gh_cuda_ctx *c, double *xyz_out)
+{
+  GH_REQUIRE(c && xyz_out, "null argument");
+  memcpy(xyz_out, c->d.sub_off, sizeof(c->d.sub_off));
+  return 0;
+}
+
+extern "C" int gh_cuda_points_to_shell_pixel(gh_cuda_ctx *c, const double *pos, const double *dz_rsd, long long n,
+                                             int *shell_out, long long *pix_out)
+{
+  GH_CTX(c);
+  GH_REQUIRE(pos && shell_out && pix_out && n >= 0, "gh_cuda_points_to_shell_pixel: bad argument");
+  if (n == 0) return 0;
+  double *d_pos = nullptr, *d_dz = nullptr;
+  int *d_sh = nullptr;
+  long long *d_px = nullptr;
+  int rc = 1;
+  do {
+    if (cudaMalloc(&d_pos, sizeof(double) * 3 * n) != cudaSuccess) break;
+    if (dz_rsd && cudaMalloc(&d_dz, sizeof(double) * n) != cudaSuccess) break;
+    if (cudaMalloc(&d_sh, sizeof(int) * n) != cudaSuccess) break;
+    if (cudaMalloc(&d_px, sizeof(long long) * n) != cudaSuccess) break;
+    if (cudaMemcpyAsync(d_pos, pos, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) break;
+    if (dz_rsd && cudaMemcpyAsync(d_dz, dz_rsd, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) break;
+    if (gh_launch_points(c, d_pos, d_dz, n, d_sh, d_px)) break;
+    if (cudaMemcpyAsync(shell_out, d_sh, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) break;
+    if (cudaMemcpyAsync(pix_out, d_px, sizeof(long long) * n, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) break;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) break;
+    rc = 0;
+  } while (0);
+  if (rc) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) gh_set_error("gh_cuda_points_to_shell_pixel: %s", cudaGetErrorString(e));
+  }
+  cudaFree(d_pos); cudaFree(d_dz); cudaFree(d_sh); cudaFree(d_px);
+  return rc;
+}
+
+extern "C" int gh_cuda_stage_times(gh_cuda_ctx *c, double *ms_out)
+{
+  GH_CTX(c);
+  GH_REQUIRE(ms_out, "null output");
+  GH_CUDA_OK(cudaStreamSynchronize(c->stream));
+  for (int s = 0; s < GH_T_NSLOTS; ++s) {
+    ms_out[s] = 0;
+    if (!c->ev_used[s]) continue;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->ev[2 * s], c->ev[2 * s + 1]) == cudaSuccess) ms_out[s] = ms;
+  }
+  return 0;
+}

@@ -1,0 +1,204 @@
+// Real-space field kernels: radial velocity, Gaussian variance, lognormal / HI-mass / RSD transform.
+// One HBM round trip each.  Float arithmetic throughout (the reference computes in double from float
+// loads and stores floats; parity is rel <= 1e-5 on the stored floats), double only for the variance sums.
+#include "gh_internal.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// radial_velocity_from_potential (reference src/fourier.c:307-373): v = +grad(phi) by central
+// differences, periodic in x and y, neighbour planes in z come from the adjacent slabs
+// (src/fourier.c:415-428), projected on the line of sight from the observer.
+// One thread per cell, x fastest; the 6 neighbour loads hit L1/L2 (three planes of phi stay in the
+// 126 MB L2 while a plane is swept), so DRAM sees ~4 B read + 4 B written per cell.
+__global__ void __launch_bounds__(256) radial_velocity_kernel(GhDev d, const float *__restrict__ vpot,
+                                                              const float *__restrict__ plane_lo,
+                                                              const float *__restrict__ plane_hi,
+                                                              float *__restrict__ rvel)
+{
+  const int ngx = 2 * d.nh;
+  const int iy = blockIdx.y, iz = blockIdx.z;
+  const float hidx = (float)(0.5 / d.dx);
+  const float y = (float)(d.dx * (iy + 0.5) - d.pos_obs[1]);
+  const float z = (float)(d.dx * (iz + d.iz0 + 0.5) - d.pos_obs[2]);
+  const int iy_hi = (iy == d.n - 1) ? 0 : iy + 1, iy_lo = (iy == 0) ? d.n - 1 : iy - 1;
+  const size_t plane = (size_t)ngx * d.n;
+  const float *p0 = vpot + (size_t)iz * plane;
+  const float *pz_lo = (iz == 0) ? plane_lo : p0 - plane;
+  const float *pz_hi = (iz == d.nz_here - 1) ? plane_hi : p0 + plane;
+  for (int ix = blockIdx.x * blockDim.x + threadIdx.x; ix < d.n; ix += gridDim.x * blockDim.x) {
+    const float x = (float)(d.dx * (ix + 0.5) - d.pos_obs[0]);
+    const int ix_hi = (ix == d.n - 1) ? 0 : ix + 1, ix_lo = (ix == 0) ? d.n - 1 : ix - 1;
+    const size_t row = (size_t)iy * ngx;
+    const float vx = hidx * (__ldg(p0 + row + ix_hi) - __ldg(p0 + row + ix_lo));
+    const float vy = hidx * (__ldg(p0 + (size_t)iy_hi * ngx + ix) - __ldg(p0 + (size_t)iy_lo * ngx + ix));
+    const float vz = hidx * (__ldg(pz_hi + row + ix) - __ldg(pz_lo + row + ix));
+    const float irr = rsqrtf(x * x + y * y + z * z);
+    rvel[(size_t)iz * plane + row + ix] = (vx * x + vy * y + vz * z) * irr;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// compute_sigma_dens (src/fourier.c:24-76): sum d and d*d (float product, double accumulation, exactly
+// the reference's promotion) over the real cells of the slab (padding skipped).  Two-stage and
+// deterministic: per-CTA partials, then one CTA folds them.
+__global__ void __launch_bounds__(256) sigma_partial_kernel(GhDev d, const float *__restrict__ dens,
+                                                            double *__restrict__ partials)
+{
+  const int ngx = 2 * d.nh;
+  const long long nrows = (long long)d.nz_here * d.n;
+  double s1 = 0.0, s2 = 0.0;
+  const int half = d.n / 2;  // rows are 8-byte aligned: read float2
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const float2 *r = reinterpret_cast<const float2 *>(dens + row * ngx);
+    for (int i = threadIdx.x; i < half; i += blockDim.x) {
+      const float2 v = __ldg(r + i);
+      s1 += (double)v.x + (double)v.y;
+      s2 += (double)__fmul_rn(v.x, v.x) + (double)__fmul_rn(v.y, v.y);
+    }
+  }
+  __shared__ double sh1[256], sh2[256];
+  sh1[threadIdx.x] = s1;
+  sh2[threadIdx.x] = s2;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sh1[threadIdx.x] += sh1[threadIdx.x + o];
+      sh2[threadIdx.x] += sh2[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partials[2 + 2 * blockIdx.x] = sh1[0];
+    partials[3 + 2 * blockIdx.x] = sh2[0];
+  }
+}
+
+__global__ void __launch_bounds__(256) sigma_final_kernel(double *__restrict__ partials, int nblocks)
+{
+  __shared__ double sh1[256], sh2[256];
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += 256) {
+    s1 += partials[2 + 2 * i];
+    s2 += partials[3 + 2 * i];
+  }
+  sh1[threadIdx.x] = s1;
+  sh2[threadIdx.x] = s2;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sh1[threadIdx.x] += sh1[threadIdx.x + o];
+      sh2[threadIdx.x] += sh2[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partials[0] = sh1[0];
+    partials[1] = sh2[0];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// get_HI (src/grid_tools.c:103-153) with z_of_r / dgrowth_of_r / vgrowth_of_r (src/cosmo.c:52-86) and
+// bias_HI / fraction_HI (src/user_defined.c:27-35), in place: dens <- HI mass, rvel <- Delta z_RSD.
+// 8 B read + 8 B written per cell; the three 5001-entry float tables are read through L1.
+__device__ __forceinline__ float lerp_tab(const float *__restrict__ tab, int ir, float t)
+{
+  const float a = __ldg(tab + ir), b = __ldg(tab + ir + 1);
+  return a + (b - a) * t;
+}
+
+__global__ void __launch_bounds__(256) get_HI_kernel(GhDev d, float *__restrict__ dens, float *__restrict__ rvel,
+                                                     float sigma2_gauss)
+{
+  const int ngx = 2 * d.nh;
+  const int iy = blockIdx.y, iz = blockIdx.z;
+  const float y = (float)(d.dx * (iy + 0.5) - d.pos_obs[1]);
+  const float z = (float)(d.dx * (iz + d.iz0 + 0.5) - d.pos_obs[2]);
+  const float mass_prefac = (float)(d.dx * d.dx * d.dx);
+  const float idr = (float)d.glob_idr, rmax = (float)d.r_tab_max;
+  const size_t base = ((size_t)iz * d.n + iy) * ngx;
+  const int last = d.nz_tab - 1;
+  // two cells per thread: rows are 8-byte aligned
+  for (int ip = blockIdx.x * blockDim.x + threadIdx.x; ip < d.n / 2; ip += gridDim.x * blockDim.x) {
+    float2 dv = *reinterpret_cast<const float2 *>(dens + base + 2 * ip);
+    float2 vv = *reinterpret_cast<const float2 *>(rvel + base + 2 * ip);
+    float dd[2] = {dv.x, dv.y}, rv[2] = {vv.x, vv.y};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float x = (float)(d.dx * (2 * ip + j + 0.5) - d.pos_obs[0]);
+      const float r = sqrtf(x * x + y * y + z * z);
+      float redshift, gd, gv;
+      if (r <= 0.f) { redshift = 0.f; gd = 1.f; gv = 1.f; }
+      else if (r >= rmax) { redshift = __ldg(d.z_r2z_f + last); gd = __ldg(d.gd_f + last); gv = __ldg(d.gv_f + last); }
+      else {
+        const float s = r * idr;
+        int ir = (int)s;
+        if (ir > last - 1) ir = last - 1;
+        const float t = s - (float)ir;
+        redshift = lerp_tab(d.z_r2z_f, ir, t);
+        gd = lerp_tab(d.gd_f, ir, t);
+        gv = lerp_tab(d.gv_f, ir, t);
+      }
+      const float opz = 1.f + redshift;
+      const float gfd = gd * (0.904f + 0.135f * powf(opz, 1.696f));                  // D(r) * b_HI(z)
+      const float dens_ln = expf(gfd * (dd[j] - 0.5f * gfd * sigma2_gauss));         // lognormal
+      dd[j] = mass_prefac * (0.008f * powf(opz, 0.6f)) * dens_ln;                    // dx^3 x_HI(z) rho_LN
+      rv[j] = rv[j] * gv;                                                            // Delta z_RSD
+    }
+    *reinterpret_cast<float2 *>(dens + base + 2 * ip) = make_float2(dd[0], dd[1]);
+    *reinterpret_cast<float2 *>(rvel + base + 2 * ip) = make_float2(rv[0], rv[1]);
+  }
+}
+
+}  // namespace
+
+int gh_launch_radial_velocity(gh_cuda_ctx *c)
+{
+  const GhDev &d = c->d;
+  const float *vpot = reinterpret_cast<const float *>(c->gridB);
+  const size_t plane = (size_t)2 * d.nh * d.n;
+  const float *lo, *hi;
+  if (d.nranks > 1) {
+    // halo exchange (src/fourier.c:415-424): last plane -> right neighbour, first plane -> left neighbour
+    const int right = (d.rank + 1) % d.nranks, left = (d.rank + d.nranks - 1) % d.nranks;
+    GH_NCCL_OK(ncclGroupStart());
+    GH_NCCL_OK(ncclSend(vpot + (size_t)(d.nz_here - 1) * plane, plane, ncclFloat, right, c->comm, c->stream));
+    GH_NCCL_OK(ncclRecv(c->halo_lo, plane, ncclFloat, left, c->comm, c->stream));
+    GH_NCCL_OK(ncclSend(vpot, plane, ncclFloat, left, c->comm, c->stream));
+    GH_NCCL_OK(ncclRecv(c->halo_hi, plane, ncclFloat, right, c->comm, c->stream));
+    GH_NCCL_OK(ncclGroupEnd());
+    lo = c->halo_lo;
+    hi = c->halo_hi;
+  } else {
+    lo = vpot + (size_t)(d.n - 1) * plane;  // src/fourier.c:425-427
+    hi = vpot;
+  }
+  dim3 grid((d.n + 255) / 256, d.n, d.nz_here);
+  radial_velocity_kernel<<<grid, 256, 0, c->stream>>>(d, vpot, lo, hi, reinterpret_cast<float *>(c->gridC));
+  GH_LAUNCH_CHECK(c);
+  return 0;
+}
+
+int gh_launch_sigma(gh_cuda_ctx *c)
+{
+  const GhDev &d = c->d;
+  int blocks = c->n_sm * 8;
+  const long long nrows = (long long)d.nz_here * d.n;
+  if (blocks > nrows) blocks = (int)nrows;
+  sigma_partial_kernel<<<blocks, 256, 0, c->stream>>>(d, reinterpret_cast<const float *>(c->gridA), c->d_partials);
+  GH_LAUNCH_CHECK(c);
+  sigma_final_kernel<<<1, 256, 0, c->stream>>>(c->d_partials, blocks);
+  GH_LAUNCH_CHECK(c);
+  return 0;
+}
+
+int gh_launch_get_HI(gh_cuda_ctx *c)
+{
+  const GhDev &d = c->d;
+  dim3 grid((d.n / 2 + 255) / 256, d.n, d.nz_here);
+  get_HI_kernel<<<grid, 256, 0, c->stream>>>(d, reinterpret_cast<float *>(c->gridA), reinterpret_cast<float *>(c->gridC),
+                                             (float)c->sigma2_gauss);
+  GH_LAUNCH_CHECK(c);
+  return 0;
+}

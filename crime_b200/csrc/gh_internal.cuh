@@ -1,0 +1,106 @@
+// Internal declarations shared by the translation units of libgh_cuda.so.
+// B200 (sm_100a) only; no CPU fallback exists anywhere in this library.
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/gh_cuda.h"
+
+#define GH_NZ_TAB_MAX 8192
+
+// Everything a kernel needs, passed by value (small tables live in device memory).
+struct GhDev {
+  int n, nh;           // n_grid, n_grid/2+1
+  int nz_here, iz0;    // real-space slab (z planes) of this rank
+  int nky_here, ky0;   // k-space slab (ky rows) of this rank, before the transpose
+  int nranks, rank;
+  double l_box, dx, pos_obs[3];
+  // k-space realisation
+  unsigned int seed;
+  int do_smoothing;
+  double r2_smooth, vfactor, dk, idk3;
+  int numk;
+  double logkmin, logkmax, idlogk, n_scal;
+  const double *logkarr, *pkarr;
+  // radial tables
+  int nz_tab;
+  double glob_idr, r_tab_max;
+  const double *z_r2z, *r_r2z, *gd, *gv;  // double, for the exact index path
+  const float *z_r2z_f, *gd_f, *gv_f;     // float copies for the field kernels
+  // sky
+  long long nside, npix;
+  int n_nu, n_nu_pad, irregular;
+  const double *nu0, *nuf;
+  double nu_min, nu_max, inv_dnu;
+  double z_lo_cull, z_hi_cull; // redshift window outside of which no sub-particle can land in a shell
+  double sub_off[3 * GH_CUDA_N_SUBPART];
+};
+
+struct gh_cuda_ctx {
+  GhDev d;
+  int device;
+  cudaStream_t stream;
+  ncclComm_t comm;
+  bool have_comm;
+  size_t slab_complex;  // complex elements per slab = nz_here*n*nh (== n*nky_here*nh)
+  float2 *gridA, *gridB, *gridC;  // dens, vpot, rvel/transposition scratch
+  float *halo_lo, *halo_hi;       // neighbour planes of vpot (nranks>1)
+  float *maps;                    // [n_nu_pad][npix]
+  float *maps_recv;               // reduce-scatter output (nranks>1)
+  float2 *twiddle;                // exp(+2 pi i j/n), j<n
+  double *d_partials;             // reduction scratch
+  double *d_prefac;               // per-shell mass->temperature factors
+  void *d_tables;                 // one allocation holding all small tables
+  size_t tables_bytes;
+  double h_prefac[4096];
+  bool k_injected;
+  bool sigma_overridden;
+  double sigma2_gauss, mean_gauss;
+  cudaEvent_t ev[2 * GH_T_NSLOTS];
+  bool ev_used[GH_T_NSLOTS];
+  unsigned long long launches;
+  int n_sm;
+};
+
+void gh_set_error(const char *fmt, ...);
+
+#define GH_CUDA_OK(call)                                                                          \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess) {                                                                     \
+      gh_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));   \
+      return 1;                                                                                   \
+    }                                                                                             \
+  } while (0)
+
+#define GH_NCCL_OK(call)                                                                          \
+  do {                                                                                            \
+    ncclResult_t r__ = (call);                                                                    \
+    if (r__ != ncclSuccess) {                                                                     \
+      gh_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, ncclGetErrorString(r__));   \
+      return 1;                                                                                   \
+    }                                                                                             \
+  } while (0)
+
+#define GH_LAUNCH_CHECK(ctx)                                                                      \
+  do {                                                                                            \
+    (ctx)->launches++;                                                                            \
+    cudaError_t e__ = cudaGetLastError();                                                         \
+    if (e__ != cudaSuccess) {                                                                     \
+      gh_set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return 1;                                                                                   \
+    }                                                                                             \
+  } while (0)
+
+// stage launchers (each enqueues on ctx->stream and returns 0 / non-zero)
+int gh_launch_kgen(gh_cuda_ctx *c);
+int gh_launch_fft_field(gh_cuda_ctx *c, float2 *field);  // full c2r of one field incl. transpose + normalisation
+int gh_fft_supported(int n);
+int gh_launch_radial_velocity(gh_cuda_ctx *c);
+int gh_launch_sigma(gh_cuda_ctx *c);  // leaves (sum, sumsq) in c->d_partials[0..1]
+int gh_launch_get_HI(gh_cuda_ctx *c);
+int gh_launch_accumulate(gh_cuda_ctx *c);
+int gh_launch_scale_maps(gh_cuda_ctx *c, float *maps, int shell0, int nshells);
+int gh_launch_points(gh_cuda_ctx *c, const double *d_pos, const double *d_dz, long long n, int *d_shell,
+                     long long *d_pix);

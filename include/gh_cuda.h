@@ -102,6 +102,11 @@ int gh_cuda_get_unique_id(void *id_out);
 int gh_cuda_create(const gh_cuda_params *params, int rank, int nranks, const void *unique_id, int device,
                    gh_cuda_ctx **ctx_out);
 
+/* Re-send the run parameters and small tables of an existing context from host memory (same n_grid,
+ * n_side, n_nu, table lengths): what read_run_params hands over before each realisation.  Lets a caller
+ * loop over seeds / spectra without re-allocating the grids. */
+int gh_cuda_set_params(gh_cuda_ctx *ctx, const gh_cuda_params *params);
+
 /* == end_fftw + the grid/map part of param_gethi_free (src/fourier.c:201, src/io_gh.c:298-324). */
 int gh_cuda_destroy(gh_cuda_ctx *ctx);
 

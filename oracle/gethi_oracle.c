@@ -17,8 +17,9 @@ double oracle_pk_linear0(const gh_cuda_params *p, double lgk)
   int ik = (int)((lgk - p->logkmin) * p->idlogk);
   if (ik < 0) return p->pkarr[0] * pow(10, p->n_scal * (lgk - p->logkmin));
   if (ik < p->numk) {
-    /* the reference reads pkarr[numk] when ik==numk-1 (lgk==logkmax exactly); mirror with a guard
-     * that returns the same value the in-bounds neighbour formula would give at that single point */
+    /* for logkmax <= lgk < logkmax + 1/idlogk the reference has ik == numk-1 and reads pkarr[numk], one
+     * past the end of its table (undefined behaviour; k >= kmax of the input file, far beyond any grid's
+     * Nyquist frequency).  The oracle clamps the upper node instead. */
     double hi = (ik + 1 < p->numk) ? p->pkarr[ik + 1] : p->pkarr[ik];
     return p->pkarr[ik] + (lgk - p->logkarr[ik]) * (hi - p->pkarr[ik]) * p->idlogk;
   }
@@ -112,8 +113,8 @@ void oracle_philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], ui
   memcpy(out, c, sizeof(c));
 }
 
-/* Product stream: counter = (global mode index lo, hi, 0, 0), key = (seed, 'GetH'); u1 = out[0]/2^32
- * (phase), u2 = out[1]/2^32 (modulus).  The global mode index is the reference's single-process index
+/* Product stream: counter = (global mode index lo, hi, 0, 0), key = (seed, 'GetH'); u1 = (out[0]>>8)/2^24
+ * (phase), u2 = (out[1]>>8)/2^24 (modulus) -- 24-bit uniforms, exact in float, u2 < 1 so ln(1-u2) is finite.  The global mode index is the reference's single-process index
  * kk + nh*(jj + n*ii) (fourier.c:278), so the realisation does not depend on the number of GPUs.
  * Rows ky in [ky0, ky0+nky).  transposed_layout=0: reference layout restricted to those rows,
  * out[(kz*nky + (ky-ky0))*nh + kx] -- for nky==n this is exactly [kz][ky][kx]. */
@@ -137,7 +138,7 @@ void oracle_kgen_philox(const gh_cuda_params *p, int ky0, int nky, float _Comple
         uint32_t ctr[4] = {(uint32_t)gidx, (uint32_t)(gidx >> 32), 0, 0}, r[4];
         oracle_philox4x32_10(ctr, key, r);
         size_t o = ((size_t)ii * nky + jl) * nh + kk;
-        mode_from_uniforms(p, k2, idk3, factor, r[0] / 4294967296.0, r[1] / 4294967296.0, &dens_k[o], &vpot_k[o]);
+        mode_from_uniforms(p, k2, idk3, factor, (r[0] >> 8) / 16777216.0, (r[1] >> 8) / 16777216.0, &dens_k[o], &vpot_k[o]);
       }
     }
   }
