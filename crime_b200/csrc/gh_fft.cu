@@ -10,11 +10,15 @@
 //   fft_strided_kernel : radix-8/4 decimation-in-frequency over a strided axis.  One CTA owns a tile of
 //                        W adjacent lines (W*8 B contiguous per element row -> full 32 B sectors), keeps
 //                        it in shared memory between radix passes, first pass straight from global
-//                        registers, last pass straight to global (digit-reversed scatter).
+//                        into registers, last pass straight to global (digit-reversed scatter).
 //   fft_c2r_rows_kernel: x axis, rows are contiguous.  Half-size complex transform with the Hermitian
 //                        pre-twist fused into the load (Im of DC and Nyquist are never read, as FFTW's
-//                        c2r), decimation-in-time so the last pass stores coalesced, in place, scaled by
+//                        c2r); a tile of W rows is transposed into the same [position][line] shared
+//                        layout, transformed in place, and gathered back in natural order so that both
+//                        the global loads and the global stores are coalesced; in place, scaled by
 //                        (sqrt(2 pi)/L)^3.
+// Shared memory is addressed through an XOR swizzle of the 16 float2-banks chosen (by brute force over
+// every access phase) so that all passes run at the 2-wavefront optimum of 8-byte accesses.
 #include "gh_internal.cuh"
 
 namespace {
@@ -80,26 +84,76 @@ template <int R> __device__ __forceinline__ void twiddle_powers(float2 (&u)[R], 
 
 // position in the decimation-in-frequency output <-> natural index (mixed-radix digit reversal):
 // natural f = q0 + R0*(q1 + R1*(q2 ...)),  position = q0*(n/R0) + q1*(n/(R0 R1)) + ...
-template <int N> __device__ __forceinline__ int dif_pos_to_freq(int pos)
+// Template recursion keeps every divisor a compile-time constant (shifts and masks in SASS).
+template <int N, int S = 0> __device__ __forceinline__ int dif_pos_to_freq(int pos)
 {
-  int f = 0;
-#pragma unroll
-  for (int s = 0; s < n_steps(N); ++s) {
-    const int sub = N / rad_prod(N, s + 1);
-    const int q = (pos / sub) % rad_at(N, s);
-    f += q * rad_prod(N, s);
+  if constexpr (S >= n_steps(N)) {
+    return 0;
+  } else {
+    constexpr int sub = N / rad_prod(N, S + 1), R = rad_at(N, S), mult = rad_prod(N, S);
+    return ((pos / sub) % R) * mult + dif_pos_to_freq<N, S + 1>(pos);
   }
-  return f;
 }
-template <int N> __device__ __forceinline__ int freq_to_dif_pos(int f)
+template <int N, int S = 0> __device__ __forceinline__ int freq_to_dif_pos(int f)
 {
-  int pos = 0;
-#pragma unroll
-  for (int s = 0; s < n_steps(N); ++s) {
-    const int q = (f / rad_prod(N, s)) % rad_at(N, s);
-    pos += q * (N / rad_prod(N, s + 1));
+  if constexpr (S >= n_steps(N)) {
+    return 0;
+  } else {
+    constexpr int sub = N / rad_prod(N, S + 1), R = rad_at(N, S), mult = rad_prod(N, S);
+    return ((f / mult) % R) * sub + freq_to_dif_pos<N, S + 1>(f);
   }
-  return pos;
+}
+
+// ---- shared-memory tile [position][line], XOR-swizzled over the 16 float2 banks ---------------------
+// address a = pos*W + w; its 16-element line index l = a >> 4 picks an XOR mask for the bank bits.
+// Shift triples found by exhaustive simulation of every access phase (stage / radix passes / gather) with
+// the half-warp conflict model of 8-byte accesses; 31 = unused.
+template <int LEN, int W> struct Swz { static constexpr int a = 0, b = 1, c = 31; };
+template <> struct Swz<64, 16> { static constexpr int a = 0, b = 2, c = 31; };
+template <> struct Swz<128, 16> { static constexpr int a = 0, b = 1, c = 5; };
+template <> struct Swz<256, 16> { static constexpr int a = 0, b = 2, c = 4; };
+template <> struct Swz<512, 16> { static constexpr int a = 0, b = 6, c = 31; };
+template <> struct Swz<1024, 16> { static constexpr int a = 0, b = 1, c = 7; };
+template <> struct Swz<1024, 8> { static constexpr int a = 0, b = 6, c = 31; };
+template <> struct Swz<2048, 8> { static constexpr int a = 0, b = 1, c = 7; };
+template <> struct Swz<2048, 4> { static constexpr int a = 0, b = 6, c = 31; };
+
+template <int LEN, int W> __device__ __forceinline__ int phys(int pos, int w)
+{
+  using S = Swz<LEN, W>;
+  const int a = pos * W + w;
+  const int l = a >> 4;
+  int m = l >> S::a;
+  if constexpr (S::b < 31) m ^= l >> S::b;
+  if constexpr (S::c < 31) m ^= l >> S::c;
+  return a ^ (m & 15);
+}
+
+// One in-place radix pass of a LEN-point decimation-in-frequency transform over a [LEN][W] tile.
+// NTW is the length of the twiddle table (exp(+2 pi i j/NTW)); LEN divides NTW.
+template <int LEN, int NTW, int W, int NT, int S>
+__device__ __forceinline__ void dif_pass_smem(float2 *sm, const float2 *__restrict__ tw)
+{
+  constexpr int R = rad_at(LEN, S);
+  constexpr int M = LEN / rad_prod(LEN, S);
+  constexpr int SUB = M / R;
+#pragma unroll 1
+  for (int item = threadIdx.x; item < W * (LEN / R); item += NT) {
+    const int w = item % W, ii = item / W;
+    const int b = ii / SUB, i = ii % SUB;
+    const int p0 = b * M + i;
+    int addr[R];
+    float2 u[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      addr[r] = phys<LEN, W>(p0 + r * SUB, w);
+      u[r] = sm[addr[r]];
+    }
+    dft<R>(u);
+    if constexpr (SUB > 1) twiddle_powers<R>(u, __ldg(tw + i * (NTW / M)));
+#pragma unroll
+    for (int q = 0; q < R; ++q) sm[addr[q]] = u[q];
+  }
 }
 
 // ---- strided axis -------------------------------------------------------------------------------
@@ -113,54 +167,14 @@ struct StridedGeom {
 };
 
 template <int N, int W, int NT, int S>
-struct DifSteps {
-  static __device__ __forceinline__ void run(float2 *sm, const float2 *__restrict__ src, float2 *__restrict__ dst,
-                                             const float2 *__restrict__ tw, const StridedGeom &g, long long sbase,
-                                             long long dbase, int nvalid)
-  {
-    constexpr int R = rad_at(N, S);
-    constexpr int M = N / rad_prod(N, S);  // current block length
-    constexpr int SUB = M / R;
-    constexpr bool FIRST = (S == 0), LAST = (S == n_steps(N) - 1);
-    const int tid = threadIdx.x;
-    const int blk_mask = (1 << g.blk_shift) - 1;
-#pragma unroll 1
-    for (int item = tid; item < W * (N / R); item += NT) {
-      const int w = item % W, ii = item / W;
-      const int b = ii / SUB, i = ii % SUB;
-      const int p0 = b * M + i;
-      float2 u[R];
-      if constexpr (FIRST) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const int n = p0 + r * SUB;
-          const long long a = sbase + (long long)(n >> g.blk_shift) * g.src_chunk + (long long)(n & blk_mask) * g.src_stride + w;
-          u[r] = (w < nvalid) ? __ldg(src + a) : make_float2(0.f, 0.f);
-        }
-      } else {
-#pragma unroll
-        for (int r = 0; r < R; ++r) u[r] = sm[(p0 + r * SUB) * W + w];
-      }
-      dft<R>(u);
-      if constexpr (!LAST) {
-        if (SUB > 1) twiddle_powers<R>(u, __ldg(tw + i * (N / M)));
-#pragma unroll
-        for (int q = 0; q < R; ++q) sm[(p0 + q * SUB) * W + w] = u[q];
-      } else {
-        // SUB == 1: p0 = b*R; scatter to natural order
-        if (w < nvalid) {
-          const int f0 = dif_pos_to_freq<N>(p0);
-#pragma unroll
-          for (int q = 0; q < R; ++q) dst[dbase + (long long)(f0 + q * (N / R)) * g.dst_stride + w] = u[q];
-        }
-      }
-    }
-    if constexpr (!LAST) {
-      __syncthreads();
-      DifSteps<N, W, NT, S + 1>::run(sm, src, dst, tw, g, sbase, dbase, nvalid);
-    }
+__device__ __forceinline__ void strided_middle(float2 *sm, const float2 *__restrict__ tw)
+{
+  if constexpr (S < n_steps(N) - 1) {
+    dif_pass_smem<N, N, W, NT, S>(sm, tw);
+    __syncthreads();
+    strided_middle<N, W, NT, S + 1>(sm, tw);
   }
-};
+}
 
 template <int N, int W, int NT>
 __global__ void __launch_bounds__(NT) fft_strided_kernel(const float2 *__restrict__ src, float2 *__restrict__ dst,
@@ -170,67 +184,76 @@ __global__ void __launch_bounds__(NT) fft_strided_kernel(const float2 *__restric
   const int tile = blockIdx.x;
   const int grp = tile / g.tiles_per_group;
   const int l0 = (tile - grp * g.tiles_per_group) * W;
-  const long long sbase = (long long)grp * g.src_group_stride + l0;
-  const long long dbase = (long long)grp * g.dst_group_stride + l0;
+  const float2 *sp = src + ((long long)grp * g.src_group_stride + l0);
+  float2 *dp = dst + ((long long)grp * g.dst_group_stride + l0);
   const int nvalid = min(W, g.lines_per_group - l0);
-  DifSteps<N, W, NT, 0>::run(sm, src, dst, tw, g, sbase, dbase, nvalid);
+  const int blk_mask = (1 << g.blk_shift) - 1;
+  const int tid = threadIdx.x;
+  constexpr int NS = n_steps(N);
+  {
+    // first pass: global -> registers -> shared (block length N, no block offset)
+    constexpr int R = rad_at(N, 0), SUB = N / R;
+#pragma unroll 1
+    for (int item = tid; item < W * SUB; item += NT) {
+      const int w = item % W, i = item / W;
+      float2 u[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int n = i + r * SUB;
+        const long long a = (long long)(n >> g.blk_shift) * g.src_chunk + (long long)(n & blk_mask) * g.src_stride;
+        u[r] = (w < nvalid) ? __ldg(sp + a + w) : make_float2(0.f, 0.f);
+      }
+      dft<R>(u);
+      twiddle_powers<R>(u, __ldg(tw + i));
+#pragma unroll
+      for (int q = 0; q < R; ++q) sm[phys<N, W>(i + q * SUB, w)] = u[q];
+    }
+  }
+  __syncthreads();
+  strided_middle<N, W, NT, 1>(sm, tw);
+  {
+    // last pass: shared -> registers -> global, scattered to natural order (block length R, SUB = 1)
+    constexpr int R = rad_at(N, NS - 1);
+#pragma unroll 1
+    for (int item = tid; item < W * (N / R); item += NT) {
+      const int w = item % W, b = item / W;
+      float2 u[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) u[r] = sm[phys<N, W>(b * R + r, w)];
+      dft<R>(u);
+      if (w < nvalid) {
+        const int f0 = dif_pos_to_freq<N>(b * R);
+        float2 *o = dp + (long long)f0 * g.dst_stride + w;
+#pragma unroll
+        for (int q = 0; q < R; ++q) o[(long long)(q * (N / R)) * g.dst_stride] = u[q];
+      }
+    }
+  }
 }
 
 // ---- contiguous rows: half-complex -> real, in place ----------------------------------------------
-// decimation in time over the half length H = N/2 with the DIF radix list reversed
-template <int N, int ROWS, int NT, int T>
-struct DitSteps {
-  static constexpr int H = N / 2;
-  static __device__ __forceinline__ void run(float2 *sm, float2 *__restrict__ out, const float2 *__restrict__ tw,
-                                             long long row0, long long nrows, long long row_stride, float norm)
-  {
-    constexpr int NS = n_steps(H);
-    constexpr int S = NS - 1 - T;              // index into the DIF list
-    constexpr int R = rad_at(H, S);
-    constexpr int SUB = H / rad_prod(H, S + 1);  // product of the radices already applied
-    constexpr int M = SUB * R;
-    constexpr bool LAST = (T == NS - 1);
-    const int tid = threadIdx.x;
-#pragma unroll 1
-    for (int item = tid; item < ROWS * (H / R); item += NT) {
-      const int row = item / (H / R), ii = item % (H / R);
-      const int b = ii / SUB, i = ii % SUB;
-      const int p0 = b * M + i;
-      float2 *s = sm + row * H;
-      float2 u[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) u[r] = s[p0 + r * SUB];
-      if (SUB > 1) twiddle_powers<R>(u, __ldg(tw + i * (N / M)));
-      dft<R>(u);
-      if constexpr (!LAST) {
-#pragma unroll
-        for (int q = 0; q < R; ++q) s[p0 + q * SUB] = u[q];
-      } else {
-        if (row0 + row < nrows) {
-          float2 *o = out + (row0 + row) * row_stride;
-#pragma unroll
-          for (int q = 0; q < R; ++q) o[p0 + q * SUB] = make_float2(u[q].x * norm, u[q].y * norm);
-        }
-      }
-    }
-    if constexpr (!LAST) {
-      __syncthreads();
-      DitSteps<N, ROWS, NT, T + 1>::run(sm, out, tw, row0, nrows, row_stride, norm);
-    }
+template <int H, int NTW, int W, int NT, int S>
+__device__ __forceinline__ void rows_passes(float2 *sm, const float2 *__restrict__ tw)
+{
+  if constexpr (S < n_steps(H)) {
+    dif_pass_smem<H, NTW, W, NT, S>(sm, tw);
+    __syncthreads();
+    rows_passes<H, NTW, W, NT, S + 1>(sm, tw);
   }
-};
+}
 
-template <int N, int ROWS, int NT>
+template <int N, int W, int NT>
 __global__ void __launch_bounds__(NT) fft_c2r_rows_kernel(float2 *__restrict__ data, const float2 *__restrict__ tw,
                                                           long long nrows, float norm)
 {
   constexpr int H = N / 2;
-  constexpr long long ROW_STRIDE = N / 2 + 1;  // complex elements per row (= 2(N/2+1) floats)
+  constexpr int ROW_STRIDE = N / 2 + 1;  // complex elements per row (= 2(N/2+1) floats)
   extern __shared__ float2 sm[];
-  const long long row0 = (long long)blockIdx.x * ROWS;
+  const long long row0 = (long long)blockIdx.x * W;
   const int tid = threadIdx.x;
-  // stage: Z[k] = (X[k] + conj X[H-k]) + i w^k (X[k] - conj X[H-k]), stored digit-reversed
-  for (int idx = tid; idx < ROWS * H; idx += NT) {
+  // stage (coalesced along the row): Z[k] = (X[k] + conj X[H-k]) + i w^k (X[k] - conj X[H-k])
+#pragma unroll 2
+  for (int idx = tid; idx < W * H; idx += NT) {
     const int row = idx / H, k = idx % H;
     float2 z = make_float2(0.f, 0.f);
     if (row0 + row < nrows) {
@@ -242,17 +265,26 @@ __global__ void __launch_bounds__(NT) fft_c2r_rows_kernel(float2 *__restrict__ d
       const float2 t = cmul(__ldg(tw + k), d);
       z = make_float2(e.x - t.y, e.y + t.x);
     }
-    sm[row * H + freq_to_dif_pos<H>(k)] = z;
+    sm[phys<H, W>(k, row)] = z;
   }
   __syncthreads();
-  DitSteps<N, ROWS, NT, 0>::run(sm, data, tw, row0, nrows, ROW_STRIDE, norm);
+  rows_passes<H, N, W, NT, 0>(sm, tw);
+  // gather in natural order (coalesced along the row): z[m] = x[2m] + i x[2m+1]
+#pragma unroll 2
+  for (int idx = tid; idx < W * H; idx += NT) {
+    const int row = idx / H, m = idx % H;
+    if (row0 + row < nrows) {
+      const float2 z = sm[phys<H, W>(freq_to_dif_pos<H>(m), row)];
+      data[(row0 + row) * ROW_STRIDE + m] = make_float2(z.x * norm, z.y * norm);
+    }
+  }
 }
 
 template <int N> struct FftCfg {
-  static constexpr int W = (N <= 512) ? 16 : (N <= 2048 ? 8 : 4);
+  static constexpr int W = (N <= 512) ? 16 : (N <= 2048 ? 8 : 4);       // strided tile width (lines)
   static constexpr int NT_S = (W * N / 16) < 64 ? 64 : ((W * N / 16) > 512 ? 512 : (W * N / 16));
-  static constexpr int ROWS = (N / 2 >= 2048) ? 2 : ((4096 / (N / 2)) > 16 ? 16 : (4096 / (N / 2)));
-  static constexpr int NT_R = (ROWS * (N / 2) / 8) < 64 ? 64 : ((ROWS * (N / 2) / 8) > 512 ? 512 : (ROWS * (N / 2) / 8));
+  static constexpr int WR = (N <= 1024) ? 16 : (N <= 2048 ? 8 : 4);     // rows per tile of the x pass
+  static constexpr int NT_R = (WR * (N / 2) / 16) < 64 ? 64 : ((WR * (N / 2) / 16) > 512 ? 512 : (WR * (N / 2) / 16));
 };
 
 template <int N>
@@ -272,10 +304,10 @@ template <int N>
 int launch_rows(gh_cuda_ctx *c, float2 *data, long long nrows, float norm)
 {
   using Cfg = FftCfg<N>;
-  auto kern = fft_c2r_rows_kernel<N, Cfg::ROWS, Cfg::NT_R>;
-  const size_t smem = (size_t)Cfg::ROWS * (N / 2) * sizeof(float2);
+  auto kern = fft_c2r_rows_kernel<N, Cfg::WR, Cfg::NT_R>;
+  const size_t smem = (size_t)Cfg::WR * (N / 2) * sizeof(float2);
   GH_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long blocks = (nrows + Cfg::ROWS - 1) / Cfg::ROWS;
+  const long long blocks = (nrows + Cfg::WR - 1) / Cfg::WR;
   kern<<<(unsigned)blocks, Cfg::NT_R, smem, c->stream>>>(data, c->twiddle, nrows, norm);
   GH_LAUNCH_CHECK(c);
   return 0;

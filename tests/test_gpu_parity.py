@@ -96,26 +96,29 @@ def test_sub_particle_offsets_match_oracle(gh32, oracle, golden_n32):
     assert np.array_equal(gh32.subparticle_offsets(), oracle.subparticle_offsets(params_of(golden_n32)))
 
 
-@pytest.mark.parametrize("nside", [16, 256, 1024, 2048])
-def test_shell_and_pixel_indices_bit_exact(oracle, tables_nu150, nside):
-    """>= 2e6 points per nside incl. polar caps, belt/cap boundary, phi wrap, shell edges, table clamps."""
-    from crime_b200 import GetHI, params_from_tables
-    p = params_from_tables(tables_nu150, n_grid=32, n_side=nside)
-    rng = np.random.default_rng(nside)
-    n = 2_000_000
-    r = rng.uniform(0.2 * float(tables_nu150["r_min"]), 1.3 * float(tables_nu150["r_max"]), n)
+def _random_points(tables, n, seed, r_lo=0.2, r_hi=1.3):
+    rng = np.random.default_rng(seed)
+    r = rng.uniform(r_lo * float(tables["r_min"]), r_hi * float(tables["r_max"]), n)
     u = rng.standard_normal((n, 3))
     u /= np.linalg.norm(u, axis=1)[:, None]
-    pos = u * r[:, None]
+    return u * r[:, None], rng.normal(0, 2e-3, n), rng
+
+
+@pytest.mark.parametrize("nside", [16, 256, 1024, 2048])
+def test_shell_and_pixel_indices_bit_exact(oracle, tables_nu150, nside):
+    """4e6 points per nside: generic directions, polar caps (both HEALPix pole formulae), belt, beyond the
+    r table.  Every shell and pixel index must equal the oracle's."""
+    from crime_b200 import GetHI, params_from_tables
+    p = params_from_tables(tables_nu150, n_grid=32, n_side=nside)
+    n = 4_000_000
+    pos, dz, rng = _random_points(tables_nu150, n, nside)
     k = n // 10
-    pos[:k, 2] = np.sign(pos[:k, 2]) * np.abs(pos[:k, 0]) * rng.uniform(50, 5000, k)      # polar caps
-    pos[k:2 * k, 2] = np.hypot(pos[k:2 * k, 0], pos[k:2 * k, 1]) * (2 / 3) / np.sqrt(1 - 4 / 9) * rng.choice([-1, 1], k) \
-        * (1 + rng.uniform(-1e-12, 1e-12, k))                                                # |cos theta| ~ 2/3
-    pos[2 * k:3 * k, 1] = rng.uniform(-1e-9, 1e-9, k)                                        # phi ~ 0 / 2 pi / pi
-    pos[3 * k, :] = [0.0, 0.0, 2000.0]
-    pos[3 * k + 1, :] = [0.0, 0.0, -2000.0]
-    pos[3 * k + 2, :] = [9000.0, 9000.0, 9000.0]                                             # beyond the r table
-    dz = rng.normal(0, 2e-3, n)
+    pos[:k, 2] = np.sign(pos[:k, 2]) * np.abs(pos[:k, 0]) * rng.uniform(5, 5000, k)      # polar caps, |cos|>0.99 too
+    pos[k, :] = [0.0, 0.0, 2000.0]
+    pos[k + 1, :] = [0.0, 0.0, -2000.0]
+    pos[k + 2, :] = [9000.0, 9000.0, 9000.0]                                             # beyond the r table
+    pos[k + 3, :] = [1500.0, 0.0, 0.0]
+    pos[k + 4, :] = [0.0, -1500.0, 0.0]
     with GetHI(p) as g:
         sh, px = g.points_to_shell_pixel(pos, dz)
     sh_o, px_o = oracle.points_to_shell_pixel(p, pos, dz)
@@ -123,6 +126,42 @@ def test_shell_and_pixel_indices_bit_exact(oracle, tables_nu150, nside):
     assert np.array_equal(px, px_o)
     inside = (sh >= 0) & (sh < p.n_nu)
     assert inside.sum() > n // 10 and (~inside).sum() > n // 10
+
+
+@pytest.mark.parametrize("nside", [16, 1024])
+def test_indices_on_pixel_edges(oracle, tables_nu150, nside):
+    """Adversarial points that sit within a few ulp of a pixel edge (phi within 1e-13 of 0, pi/2, pi;
+    |cos theta| within 1e-12 of 2/3).  There the answer hinges on the last bit of atan2 / the division,
+    which libm implementations do not agree on (glibc and CUDA both document <= 1-2 ulp), so the
+    requirement is: identical shells, and every pixel either equal to the oracle's or equal to the
+    oracle's pixel for the same point rotated by +-1e-15 rad about z (i.e. the neighbouring pixel across
+    the edge the point sits on) -- and that must be rare."""
+    from crime_b200 import GetHI, params_from_tables
+    p = params_from_tables(tables_nu150, n_grid=32, n_side=nside)
+    n = 600_000
+    pos, dz, rng = _random_points(tables_nu150, n, 7 + nside, 0.9, 1.0)
+    k = n // 3
+    pos[:k, 2] = np.hypot(pos[:k, 0], pos[:k, 1]) * (2 / 3) / np.sqrt(1 - 4 / 9) * rng.choice([-1, 1], k) \
+        * (1 + rng.uniform(-1e-12, 1e-12, k))                                            # |cos theta| ~ 2/3
+    pos[k:2 * k, 1] = rng.uniform(-1e-9, 1e-9, k)                                        # phi ~ 0 / 2 pi / pi
+    pos[2 * k:, 0] = rng.uniform(-1e-9, 1e-9, n - 2 * k)                                 # phi ~ +- pi/2
+    with GetHI(p) as g:
+        sh, px = g.points_to_shell_pixel(pos, dz)
+    sh_o, px_o = oracle.points_to_shell_pixel(p, pos, dz)
+    assert np.array_equal(sh, sh_o)
+    bad = np.nonzero(px != px_o)[0]
+    assert len(bad) <= n // 20000
+    if len(bad):
+        eps = 1e-15
+        for sgn in (+1, -1):
+            rot = pos[bad].copy()
+            rot[:, 0] = pos[bad, 0] - sgn * eps * pos[bad, 1]
+            rot[:, 1] = pos[bad, 1] + sgn * eps * pos[bad, 0]
+            _, alt = oracle.points_to_shell_pixel(p, rot, dz[bad])
+            bad = bad[px[bad] != alt]
+            if not len(bad):
+                break
+        assert not len(bad), f"{len(bad)} pixel mismatches not explained by an edge within 1e-15 rad"
 
 
 def test_regular_nutable_personality(oracle, tables_nu150):
@@ -151,10 +190,8 @@ def test_kgen_matches_oracle_philox(oracle, tables_nu64, n_grid):
         g.generate_k()
         dk, vk = g.download_delta_k()
     dk_o, vk_o = oracle.kgen_philox(p)
-    scale = np.abs(dk_o).max(axis=2, keepdims=True) + 1e-30
     # element-wise against the modulus of the same mode
     m = np.abs(dk_o) > 0
-    assert np.abs(dk - dk_o)[m].max() / np.abs(dk_o)[m].min() < 1 or True
     assert (np.abs(dk - dk_o)[m] / np.abs(dk_o)[m]).max() < TOL
     assert (np.abs(vk - vk_o)[m] / np.abs(vk_o)[m]).max() < TOL
     assert dk[0, 0, 0] == 0 and vk[0, 0, 0] == 0
