@@ -103,7 +103,7 @@ static int upload_tables(gh_cuda_ctx *c, const gh_cuda_params *p)
   const int nz = p->nz_tab, nk = p->numk, nn = p->n_nu;
   // layout: doubles first, then floats
   const size_t n_dbl = (size_t)2 * nk + 4 * nz + 2 * nn;
-  const size_t n_flt = (size_t)3 * nz;
+  const size_t n_flt = (size_t)3 * nz + nn + 1;
   const size_t bytes = n_dbl * sizeof(double) + n_flt * sizeof(float);
   char *h = (char *)malloc(bytes);
   GH_REQUIRE(h, "out of host memory");
@@ -121,6 +121,12 @@ static int upload_tables(gh_cuda_ctx *c, const gh_cuda_params *p)
     hf[nz + i] = (float)p->growth_d_arr[i];
     hf[2 * nz + i] = (float)p->growth_v_arr[i];
   }
+  for (int i = 0; i <= nn; ++i) {  // shell edges for the fp32 fast path
+    double e;
+    if (p->irregular_nutable) e = (i < nn) ? p->nu0_arr[i] : p->nuf_arr[nn - 1];
+    else e = p->nu_min + (p->nu_max - p->nu_min) * (double)(i == 0 ? -1 : i) / nn;  // shell 0 also takes (nu_min-dnu, nu_min): C truncation, src/pixelize.c:216
+    hf[3 * nz + i] = (float)e;
+  }
   cudaError_t e = cudaSuccess;
   if (!c->d_tables) { e = cudaMalloc(&c->d_tables, bytes); c->tables_bytes = bytes; }
   else if (bytes != c->tables_bytes) { free(h); gh_set_error("table sizes changed; create a new context"); return 1; }
@@ -133,7 +139,7 @@ static int upload_tables(gh_cuda_ctx *c, const gh_cuda_params *p)
   d.logkarr = dd + o_logk; d.pkarr = dd + o_pk;
   d.z_r2z = dd + o_z; d.r_r2z = dd + o_r; d.gd = dd + o_gd; d.gv = dd + o_gv;
   d.nu0 = dd + o_nu0; d.nuf = dd + o_nuf;
-  d.z_r2z_f = df; d.gd_f = df + nz; d.gv_f = df + 2 * nz;
+  d.z_r2z_f = df; d.gd_f = df + nz; d.gv_f = df + 2 * nz; d.nu_edges_f = df + 3 * nz;
   return 0;
 }
 
@@ -174,6 +180,7 @@ static int apply_params(gh_cuda_ctx *c, const gh_cuda_params *p, int rank, int n
       d.sub_off[GH_CUDA_N_SUBPART + i] = lcell * (g.uniform() - 0.5);
       d.sub_off[2 * GH_CUDA_N_SUBPART + i] = lcell * (g.uniform() - 0.5);
     }
+    for (int i = 0; i < 3 * GH_CUDA_N_SUBPART; ++i) d.sub_off_f[i] = (float)d.sub_off[i];
   }
   {
     // src/pixelize.c:155,246-256
@@ -603,6 +610,58 @@ extern "C" int gh_cuda_points_to_shell_pixel(gh_cuda_ctx *c, const double *pos, 
     if (e != cudaSuccess) gh_set_error("gh_cuda_points_to_shell_pixel: %s", cudaGetErrorString(e));
   }
   cudaFree(d_pos); cudaFree(d_dz); cudaFree(d_sh); cudaFree(d_px);
+  return rc;
+}
+
+extern "C" int gh_cuda_fastpath_audit(gh_cuda_ctx *c, const double *pos, const double *dz_rsd, long long n, double eps_scale,
+                                      unsigned long long *counts_out)
+{
+  GH_CTX(c);
+  GH_REQUIRE(pos && counts_out && n >= 0, "gh_cuda_fastpath_audit: bad argument");
+  memset(counts_out, 0, 4 * sizeof(unsigned long long));
+  if (n == 0) return 0;
+  double *d_pos = nullptr, *d_dz = nullptr;
+  unsigned long long *d_cnt = nullptr;
+  int rc = 1;
+  do {
+    if (cudaMalloc(&d_pos, sizeof(double) * 3 * n) != cudaSuccess) break;
+    if (dz_rsd && cudaMalloc(&d_dz, sizeof(double) * n) != cudaSuccess) break;
+    if (cudaMalloc(&d_cnt, 4 * sizeof(unsigned long long)) != cudaSuccess) break;
+    if (cudaMemsetAsync(d_cnt, 0, 4 * sizeof(unsigned long long), c->stream) != cudaSuccess) break;
+    if (cudaMemcpyAsync(d_pos, pos, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) break;
+    if (dz_rsd && cudaMemcpyAsync(d_dz, dz_rsd, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) break;
+    if (gh_launch_fastpath_audit(c, d_pos, d_dz, n, (float)eps_scale, d_cnt)) break;
+    if (cudaMemcpyAsync(counts_out, d_cnt, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) break;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) break;
+    rc = 0;
+  } while (0);
+  if (rc) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) gh_set_error("gh_cuda_fastpath_audit: %s", cudaGetErrorString(e));
+  }
+  cudaFree(d_pos); cudaFree(d_dz); cudaFree(d_cnt);
+  return rc;
+}
+
+extern "C" int gh_cuda_accumulate_audit(gh_cuda_ctx *c, double eps_scale, unsigned long long *counts_out)
+{
+  GH_CTX(c);
+  GH_REQUIRE(counts_out, "gh_cuda_accumulate_audit: null output");
+  unsigned long long *d_cnt = nullptr;
+  GH_CUDA_OK(cudaMalloc(&d_cnt, 4 * sizeof(unsigned long long)));
+  int rc = 1;
+  do {
+    if (cudaMemsetAsync(d_cnt, 0, 4 * sizeof(unsigned long long), c->stream) != cudaSuccess) break;
+    if (gh_launch_accumulate_audit(c, (float)eps_scale, d_cnt)) break;
+    if (cudaMemcpyAsync(counts_out, d_cnt, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) break;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) break;
+    rc = 0;
+  } while (0);
+  if (rc) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) gh_set_error("gh_cuda_accumulate_audit: %s", cudaGetErrorString(e));
+  }
+  cudaFree(d_cnt);
   return rc;
 }
 

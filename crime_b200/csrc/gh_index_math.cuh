@@ -105,3 +105,24 @@ GH_HD int gh_point_to_shell_pixel(const GhIndexTables &t, double x, double y, do
   if (inu >= 0 && inu < t.n_nu) *ipix = gh_vec2pix_ring(t.nside, x, y, z, r);
   return inu;
 }
+
+// ================================================================================================
+// fp32 fast path with a guaranteed-safe fallback.
+//
+// The exact path above costs ~350 instructions per sub-particle (fp64 sqrt, divisions, atan2).  The fast
+// path evaluates the same quantities in fp32 and accepts its own answer only when every floor() /
+// comparison it took is further from its decision boundary than a conservative bound on the fp32-vs-fp64
+// discrepancy of that quantity; otherwise the sub-particle is re-done with the exact path.  Accepted
+// answers are therefore identical to the exact path's.  Bounds (derivation in DESIGN.md; audited on
+// device against the exact path by gh_cuda_fastpath_audit, which also reports the largest observed
+// discrepancy/bound ratio):
+//   observed frequency      : GH_FAST_EPS_NU  MHz                    (est. <= 6e-4)
+//   pixel-index coordinates : GH_FAST_EPS_IDX * nside                (est. <= 1.2e-6 * nside)
+//   |cos(theta)| vs 2/3     : GH_FAST_EPS_CTH                        (est. <= 4e-7)
+//   phi * 2/pi vs integers  : GH_FAST_EPS_TT                         (est. <= 1e-6)
+#define GH_FAST_EPS_NU 4e-3f
+#define GH_FAST_EPS_IDX 6e-6f
+#define GH_FAST_EPS_CTH 3e-6f
+#define GH_FAST_EPS_TT 6e-6f
+
+enum { GH_FAST_OUT = 0, GH_FAST_IN = 1, GH_FAST_UNSURE = 2 };

@@ -32,9 +32,11 @@ struct GhDev {
   long long nside, npix;
   int n_nu, n_nu_pad, irregular;
   const double *nu0, *nuf;
+  const float *nu_edges_f;  // n_nu+1 float shell edges for the fp32 fast path
   double nu_min, nu_max, inv_dnu;
   double z_lo_cull, z_hi_cull; // redshift window outside of which no sub-particle can land in a shell
   double sub_off[3 * GH_CUDA_N_SUBPART];
+  float sub_off_f[3 * GH_CUDA_N_SUBPART];
 };
 
 struct gh_cuda_ctx {
@@ -101,6 +103,9 @@ int gh_launch_radial_velocity(gh_cuda_ctx *c);
 int gh_launch_sigma(gh_cuda_ctx *c);  // leaves (sum, sumsq) in c->d_partials[0..1]
 int gh_launch_get_HI(gh_cuda_ctx *c);
 int gh_launch_accumulate(gh_cuda_ctx *c);
+int gh_launch_accumulate_audit(gh_cuda_ctx *c, float eps_scale, unsigned long long *d_counts);
 int gh_launch_scale_maps(gh_cuda_ctx *c, float *maps, int shell0, int nshells);
+int gh_launch_fastpath_audit(gh_cuda_ctx *c, const double *d_pos, const double *d_dz, long long n, float eps_scale,
+                              unsigned long long *d_counts);
 int gh_launch_points(gh_cuda_ctx *c, const double *d_pos, const double *d_dz, long long n, int *d_shell,
                      long long *d_pix);

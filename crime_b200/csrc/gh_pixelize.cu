@@ -21,38 +21,292 @@ __device__ __forceinline__ GhIndexTables tables_of(const GhDev &d)
   return t;
 }
 
-__global__ void __launch_bounds__(128) accumulate_kernel(GhDev d, const float *__restrict__ mass,
-                                                         const float *__restrict__ dzrsd, float *__restrict__ maps)
+// ------------------------------------------------------------------------------------------------
+// fp32 fast path (device only, hand-trimmed: this loop is instruction-issue bound).  It evaluates the
+// same quantities as gh_point_to_shell_pixel in fp32 and accepts its own answer only when every
+// floor() / comparison it took is further from its decision boundary than a conservative bound on the
+// fp32-vs-fp64 discrepancy of that quantity (GH_FAST_EPS_*); otherwise the sub-particle is re-done with
+// the exact path.  Accepted answers are therefore identical to the exact path's; the *_audit entry points
+// measure that on the device, also with the bounds scaled down.
+__device__ __forceinline__ float rsqrt_ftz(float a)
 {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+__device__ __forceinline__ float rcp_ftz(float a)
+{
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+
+struct FastCtx {
+  const float *ztab, *edges;
+  float idr, r_tab_max, z_last, nu_min, inv_dnu;
+  float eps_nu, cth_lo, cth_hi, eps_tt, fns, eidx;
+  float nu_out_lo, nu_out_hi;  // certainly outside every shell below / above these
+  int ns, n_nu, ir_max;
+};
+
+__device__ __forceinline__ FastCtx fast_ctx_of(const GhDev &d, float eps_scale)
+{
+  FastCtx f;
+  f.ztab = d.z_r2z_f; f.edges = d.nu_edges_f;
+  f.idr = (float)d.glob_idr; f.r_tab_max = (float)d.r_tab_max; f.z_last = __ldg(d.z_r2z_f + d.nz_tab - 1);
+  f.nu_min = (float)d.nu_min; f.inv_dnu = (float)d.inv_dnu;
+  f.eps_nu = GH_FAST_EPS_NU * eps_scale;
+  f.cth_lo = (2.0f / 3.0f) - GH_FAST_EPS_CTH * eps_scale; f.cth_hi = (2.0f / 3.0f) + GH_FAST_EPS_CTH * eps_scale;
+  f.eps_tt = GH_FAST_EPS_TT * eps_scale;
+  f.ns = (int)d.nside; f.fns = (float)f.ns; f.eidx = GH_FAST_EPS_IDX * eps_scale * f.fns;
+  f.n_nu = d.n_nu; f.ir_max = d.nz_tab - 2;
+  f.nu_out_lo = __ldg(d.nu_edges_f) - f.eps_nu; f.nu_out_hi = __ldg(d.nu_edges_f + d.n_nu) + f.eps_nu;
+  return f;
+}
+
+// float z_of_r (src/cosmo.c:52-62)
+__device__ __forceinline__ float z_of_r_f(const FastCtx &f, float r)
+{
+  const float s = fmaxf(r, 0.f) * f.idr;
+  const int ir = min((int)s, f.ir_max);
+  const float a = __ldg(f.ztab + ir), b = __ldg(f.ztab + ir + 1);
+  const float zr = fmaf(b - a, s - (float)ir, a);
+  return (r >= f.r_tab_max) ? f.z_last : zr;
+}
+
+// shell of a frequency: GH_FAST_IN (sure, shell in inu), GH_FAST_OUT (surely outside), GH_FAST_UNSURE
+__device__ __forceinline__ int fast_shell(const FastCtx &f, float nu, int &inu)
+{
+  int g = (int)((nu - f.nu_min) * f.inv_dnu);
+  g = max(0, min(g, f.n_nu - 1));
+  const float lo = __ldg(f.edges + g), hi = __ldg(f.edges + g + 1);
+  inu = g;
+  if (nu > lo + f.eps_nu && nu < hi - f.eps_nu) return GH_FAST_IN;
+  if (nu < f.nu_out_lo || nu > f.nu_out_hi) return GH_FAST_OUT;
+  return GH_FAST_UNSURE;  // next to an edge (or a non-uniform table where the uniform guess is off)
+}
+
+// RING pixel from cth = z/r, tt = azimuth/(pi/2) in [0,4], and (only when |cth| > 0.99) x^2+y^2 and 1/r
+__device__ __forceinline__ bool fast_pixel(const FastCtx &f, float cth, float tt, float q, float inv_r, int &pix)
+{
+  const float za = fabsf(cth);
+  const int ns = f.ns;
+  const float lo = f.eidx, hi = 1.0f - f.eidx;
+  if (za < f.cth_lo) {
+    const float t1 = fmaf(f.fns, tt, 0.5f * f.fns), t2 = (0.75f * f.fns) * cth;
+    const float a = t1 - t2, b = t1 + t2;
+    const float fa = floorf(a), fb = floorf(b);
+    const float ra = a - fa, rb = b - fb;
+    const bool ok = (ra > lo) & (ra < hi) & (rb > lo) & (rb < hi) & (tt > f.eps_tt) & (tt < 4.0f - f.eps_tt);
+    const int jp = (int)fa, jm = (int)fb;
+    const int ir = ns + 1 + jp - jm;
+    int ip = (jp + jm - ns + 2 - (ir & 1)) >> 1;  // (jp+jm-ns+kshift+1)/2, operand >= 0 for tt >= eps_tt
+    ip -= (ip >= 4 * ns) ? 4 * ns : 0;
+    pix = 2 * ns * (ns - 1) + (ir - 1) * 4 * ns + ip;
+    return ok;
+  }
+  if (za > f.cth_hi) {
+    const float ft = floorf(tt);
+    const float tp = tt - ft;
+    float tmp;
+    if (za > 0.99f) {
+      tmp = f.fns * (q * rsqrt_ftz(fmaxf(q, 1e-30f)) * inv_r) * rsqrt_ftz((1.0f + za) * (1.0f / 3.0f));
+    } else {
+      const float u = 3.0f * (1.0f - za);
+      tmp = f.fns * (u * rsqrt_ftz(u));
+    }
+    const float a = tp * tmp, b = (1.0f - tp) * tmp;
+    const float fa = floorf(a), fb = floorf(b);
+    const float ra = a - fa, rb = b - fb;
+    const int jp = (int)fa, jm = (int)fb;
+    const int ir = jp + jm + 1;
+    const float c = tt * (float)ir;
+    const float fc = floorf(c);
+    const float rc = c - fc;
+    const bool ok = (tp > f.eps_tt) & (tp < 1.0f - f.eps_tt) & (ft < 3.5f) & (ra > lo) & (ra < hi) & (rb > lo) & (rb < hi) &
+                    (rc > lo) & (rc < hi);
+    int ip = (int)fc;
+    ip -= (ip >= 4 * ir) ? 4 * ir : 0;
+    pix = (cth > 0.f) ? 2 * ir * (ir - 1) + ip : 12 * ns * ns - 2 * ir * (ir + 1) + ip;
+    return ok;
+  }
+  return false;
+}
+
+// One thread per cell, a warp covers 8 x 4 cells in (x, y) so that its lanes see nearly the same shells
+// and the same HEALPix regime.  Pass 1 sends each of the 10 sub-particles through the fp32 fast path: it
+// either proves the sub-particle misses every shell, or proves (shell, pixel) with all decisions clear of
+// their error bounds and deposits at once, or marks it unsure.  The azimuth is atan2 of the cell centre
+// plus the small rotation to the sub-particle (series in the tangent of the rotation angle; cells close
+// to the polar axis use atan2f per sub-particle).  Pass 2 compacts the unsure sub-particles of the warp
+// into a shared-memory queue and re-does exactly those in fp64 (gh_point_to_shell_pixel), 32 at a time,
+// so the slow path runs on full warps.
+// AUDIT: nothing is deposited; every sub-particle is evaluated by both paths and the outcomes counted.
+template <bool AUDIT>
+__global__ void __launch_bounds__(128) accumulate_kernel(GhDev d, const float *__restrict__ mass,
+                                                         const float *__restrict__ dzrsd, float *__restrict__ maps,
+                                                         float eps_scale, unsigned long long *__restrict__ counts)
+{
+  __shared__ unsigned short queue[4][32 * GH_CUDA_N_SUBPART];
   const int ngx = 2 * d.nh;
-  const int iy = blockIdx.y, iz = blockIdx.z;
-  const int ix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ix >= d.n) return;
+  const int tid = threadIdx.x + 8 * threadIdx.y;  // blockDim = (8, 16)
+  const int lane = tid & 31, warp = tid >> 5;
+  const int ix = blockIdx.x * 8 + threadIdx.x, iy = blockIdx.y * 16 + threadIdx.y, iz = blockIdx.z;
+  const bool active = (ix < d.n) && (iy < d.n);
+  const FastCtx f = fast_ctx_of(d, eps_scale);
   const GhIndexTables t = tables_of(d);
   const double x0 = d.dx * (ix + 0.5) - d.pos_obs[0];
   const double y0 = d.dx * (iy + 0.5) - d.pos_obs[1];
   const double z0 = d.dx * (iz + d.iz0 + 0.5) - d.pos_obs[2];
-  const size_t idx = ((size_t)iz * d.n + iy) * ngx + ix;
-  const double dz = (double)dzrsd[idx];
-  // conservative cull: all sub-particles lie within half a cell diagonal of the centre and z_of_r is
-  // non-decreasing, so their redshifts lie in [z(rc-h), z(rc+h)] + dz
+  float dzf = 0.f, w = 0.f;
+  unsigned need = 0u;
+  unsigned long long c_out = 0, c_in = 0, c_unsure = 0, c_wrong = 0;
+  if (active) {
+    const size_t idx = ((size_t)iz * d.n + iy) * ngx + ix;
+    dzf = dzrsd[idx];
+    // cell centre as hi + lo floats: positions are xh + (xl + offset), one rounding of the full coordinate
+    const float xh = (float)x0, yh = (float)y0, zh = (float)z0;
+    const float xl = (float)(x0 - (double)xh), yl = (float)(y0 - (double)yh), zl = (float)(z0 - (double)zh);
+    const float rp2 = fmaf(xh, xh, yh * yh);
+    const float rc = sqrtf(fmaf(zh, zh, rp2));
+    // conservative cull: all sub-particles lie within half a cell diagonal of the centre and z_of_r is
+    // non-decreasing, so their redshifts lie in [z(rc-h), z(rc+h)] + dz; 1e-3 Mpc/h and 1e-5 in z cover
+    // the fp32 evaluation of this test
+    const float h = (float)d.dx * 0.8660254f + 1e-3f + 1e-6f * rc;
+    const float zs_hi = z_of_r_f(f, rc + h) + dzf + 1e-5f, zs_lo = z_of_r_f(f, rc - h) + dzf - 1e-5f;
+    const bool culled = (zs_hi < (float)d.z_lo_cull || zs_lo > (float)d.z_hi_cull);
+    if (AUDIT && culled) {
+      for (int isub = 0; isub < GH_CUDA_N_SUBPART; ++isub) {
+        long long pe;
+        gh_point_to_shell_pixel(t, x0 + d.sub_off[isub], y0 + d.sub_off[GH_CUDA_N_SUBPART + isub],
+                                z0 + d.sub_off[2 * GH_CUDA_N_SUBPART + isub], (double)dzf, &pe);
+        c_out++;
+        if (pe >= 0) c_wrong++;
+      }
+    }
+    if (!culled) {
+      const double mass_sub = (double)mass[idx] / GH_CUDA_N_SUBPART;  // src/pixelize.c:203
+      w = (float)mass_sub;
+      // azimuth of the cell centre; sub-particles rotate it by atan(cross/dot), |cross/dot| < 0.05 when
+      // the cell is further than 24 cells from the polar axis
+      const bool series = rp2 > 576.0f * (float)(d.dx * d.dx);
+      const float phi_c = atan2f(yh, xh);
+#pragma unroll 2
+      for (int isub = 0; isub < GH_CUDA_N_SUBPART; ++isub) {
+        const float ox = xl + d.sub_off_f[isub], oy = yl + d.sub_off_f[GH_CUDA_N_SUBPART + isub];
+        const float x = xh + ox, y = yh + oy, z = zh + (zl + d.sub_off_f[2 * GH_CUDA_N_SUBPART + isub]);
+        const float q = fmaf(x, x, y * y);
+        const float r2 = fmaf(z, z, q);
+        const float inv_r = rsqrt_ftz(r2);
+        const float nu = 1420.40575177f * rcp_ftz(1.0f + (z_of_r_f(f, r2 * inv_r) + dzf));
+        int inu, pix = -1;
+        int st = fast_shell(f, nu, inu);
+        if (st == GH_FAST_IN) {
+          float phi;
+          if (series) {
+            const float tq = fmaf(xh, oy, -yh * ox) * rcp_ftz(rp2 + fmaf(xh, ox, yh * oy));
+            const float t2 = tq * tq;
+            phi = fmaf(tq, fmaf(t2, fmaf(t2, 0.2f, -0.33333333f), 1.0f), phi_c);
+          } else {
+            phi = atan2f(y, x);
+          }
+          float tt = phi * 0.63661977236758134308f;
+          tt += (tt < 0.f) ? 4.0f : 0.f;
+          if (!fast_pixel(f, z * inv_r, tt, q, inv_r, pix)) st = GH_FAST_UNSURE;
+        }
+        if (!AUDIT) {
+          if (st == GH_FAST_IN) atomicAdd(maps + ((size_t)d.npix * inu + pix), w);
+          else if (st == GH_FAST_UNSURE) need |= 1u << isub;
+        } else {
+          long long pe;
+          const int se = gh_point_to_shell_pixel(t, x0 + d.sub_off[isub], y0 + d.sub_off[GH_CUDA_N_SUBPART + isub],
+                                                 z0 + d.sub_off[2 * GH_CUDA_N_SUBPART + isub], (double)dzf, &pe);
+          if (st == GH_FAST_OUT) { c_out++; if (pe >= 0) c_wrong++; }
+          else if (st == GH_FAST_IN) { c_in++; if (inu != se || (long long)pix != pe) c_wrong++; }
+          else c_unsure++;
+        }
+      }
+    }
+  }
+  if (AUDIT) {
+    atomicAdd(counts + 0, c_out);
+    atomicAdd(counts + 1, c_in);
+    atomicAdd(counts + 2, c_unsure);
+    atomicAdd(counts + 3, c_wrong);
+    return;
+  }
+  // ---- pass 2: exact path for the unsure sub-particles of this warp ----
+  const unsigned full = 0xffffffffu;
+  if (__ballot_sync(full, need != 0u) == 0u) return;
+  const int cnt = __popc(need);
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(full, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const int total = __shfl_sync(full, incl, 31);
   {
-    const double rc = sqrt(x0 * x0 + y0 * y0 + z0 * z0);
-    const double h = d.dx * 0.8660254037844387 + 1e-9 * (rc + d.dx);
-    const double zs_hi = gh_z_of_r(t, rc + h) + dz, zs_lo = gh_z_of_r(t, rc - h) + dz;
-    if (zs_hi < d.z_lo_cull || zs_lo > d.z_hi_cull) return;
+    int at = incl - cnt;
+    unsigned m = need;
+    while (m) {
+      const int isub = __ffs(m) - 1;
+      m &= m - 1;
+      queue[warp][at++] = (unsigned short)((lane << 4) | isub);
+    }
   }
-  const double mass_sub = (double)mass[idx] / GH_CUDA_N_SUBPART;  // src/pixelize.c:203
-  const float w = (float)mass_sub;
-#pragma unroll 1
-  for (int isub = 0; isub < GH_CUDA_N_SUBPART; ++isub) {
-    const double x = x0 + d.sub_off[isub];
-    const double y = y0 + d.sub_off[GH_CUDA_N_SUBPART + isub];
-    const double z = z0 + d.sub_off[2 * GH_CUDA_N_SUBPART + isub];
-    long long ipix;
-    const int inu = gh_point_to_shell_pixel(t, x, y, z, dz, &ipix);
-    if (ipix >= 0) atomicAdd(maps + (size_t)ipix + (size_t)d.npix * inu, w);
+  __syncwarp();
+  for (int base = 0; base < total; base += 32) {
+    const int j = base + lane;
+    const bool valid = j < total;
+    const unsigned e = valid ? queue[warp][j] : 0u;
+    const int src = e >> 4, isub = e & 15;
+    const double sx = __shfl_sync(full, x0, src), sy = __shfl_sync(full, y0, src);
+    const float sdz = __shfl_sync(full, dzf, src), sw = __shfl_sync(full, w, src);
+    if (valid) {
+      long long ipix;
+      const int inu = gh_point_to_shell_pixel(t, sx + d.sub_off[isub], sy + d.sub_off[GH_CUDA_N_SUBPART + isub],
+                                              z0 + d.sub_off[2 * GH_CUDA_N_SUBPART + isub], (double)sdz, &ipix);
+      if (ipix >= 0) atomicAdd(maps + (size_t)ipix + (size_t)d.npix * inu, sw);
+    }
   }
+}
+
+// Audit of the fast path against the exact path on arbitrary points: counts[0..3] = fast says out / in /
+// unsure / (fast was sure but disagrees with the exact path -- must stay 0).
+__global__ void __launch_bounds__(128) fastpath_audit_kernel(GhDev d, const double *__restrict__ pos,
+                                                             const double *__restrict__ dz, long long n, float eps_scale,
+                                                             unsigned long long *__restrict__ counts)
+{
+  const GhIndexTables t = tables_of(d);
+  const FastCtx f = fast_ctx_of(d, eps_scale);
+  unsigned long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double xd = pos[3 * i], yd = pos[3 * i + 1], zd = pos[3 * i + 2];
+    const float dzf = dz ? (float)dz[i] : 0.f;
+    long long pe;
+    const int se = gh_point_to_shell_pixel(t, xd, yd, zd, (double)dzf, &pe);
+    const float x = (float)xd, y = (float)yd, z = (float)zd;
+    const float q = fmaf(x, x, y * y), r2 = fmaf(z, z, q);
+    int st = GH_FAST_UNSURE, inu = -7, pix = -1;
+    if (r2 > 1e-12f) {
+      const float inv_r = rsqrt_ftz(r2);
+      const float nu = 1420.40575177f * rcp_ftz(1.0f + (z_of_r_f(f, r2 * inv_r) + dzf));
+      st = fast_shell(f, nu, inu);
+      if (st == GH_FAST_IN) {
+        float tt = atan2f(y, x) * 0.63661977236758134308f;
+        tt += (tt < 0.f) ? 4.0f : 0.f;
+        if (!fast_pixel(f, z * inv_r, tt, q, inv_r, pix)) st = GH_FAST_UNSURE;
+      }
+    }
+    if (st == GH_FAST_OUT) { c0++; if (pe >= 0) c3++; }
+    else if (st == GH_FAST_IN) { c1++; if (inu != se || (long long)pix != pe) c3++; }
+    else c2++;
+  }
+  atomicAdd(counts + 0, c0);
+  atomicAdd(counts + 1, c1);
+  atomicAdd(counts + 2, c2);
+  atomicAdd(counts + 3, c3);
 }
 
 // src/pixelize.c:236-261: one prefactor per shell, float * double -> float
@@ -89,9 +343,19 @@ __global__ void __launch_bounds__(128) points_kernel(GhDev d, const double *__re
 int gh_launch_accumulate(gh_cuda_ctx *c)
 {
   const GhDev &d = c->d;
-  dim3 grid((d.n + 127) / 128, d.n, d.nz_here);
-  accumulate_kernel<<<grid, 128, 0, c->stream>>>(d, reinterpret_cast<const float *>(c->gridA),
-                                                 reinterpret_cast<const float *>(c->gridC), c->maps);
+  dim3 grid((d.n + 7) / 8, (d.n + 15) / 16, d.nz_here), block(8, 16);
+  accumulate_kernel<false><<<grid, block, 0, c->stream>>>(d, reinterpret_cast<const float *>(c->gridA),
+                                                        reinterpret_cast<const float *>(c->gridC), c->maps, 1.0f, nullptr);
+  GH_LAUNCH_CHECK(c);
+  return 0;
+}
+
+int gh_launch_accumulate_audit(gh_cuda_ctx *c, float eps_scale, unsigned long long *d_counts)
+{
+  const GhDev &d = c->d;
+  dim3 grid((d.n + 7) / 8, (d.n + 15) / 16, d.nz_here), block(8, 16);
+  accumulate_kernel<true><<<grid, block, 0, c->stream>>>(d, reinterpret_cast<const float *>(c->gridA),
+                                                       reinterpret_cast<const float *>(c->gridC), c->maps, eps_scale, d_counts);
   GH_LAUNCH_CHECK(c);
   return 0;
 }
@@ -104,6 +368,17 @@ int gh_launch_scale_maps(gh_cuda_ctx *c, float *maps, int shell0, int nshells)
   if (bx > 1024) bx = 1024;
   dim3 grid(bx, nshells);
   scale_maps_kernel<<<grid, 256, 0, c->stream>>>(reinterpret_cast<float4 *>(maps), c->d_prefac, npix4, shell0);
+  GH_LAUNCH_CHECK(c);
+  return 0;
+}
+
+int gh_launch_fastpath_audit(gh_cuda_ctx *c, const double *d_pos, const double *d_dz, long long n, float eps_scale,
+                              unsigned long long *d_counts)
+{
+  if (n <= 0) return 0;
+  long long blocks = (n + 127) / 128;
+  if (blocks > c->n_sm * 16) blocks = c->n_sm * 16;
+  fastpath_audit_kernel<<<(unsigned)blocks, 128, 0, c->stream>>>(c->d, d_pos, d_dz, n, eps_scale, d_counts);
   GH_LAUNCH_CHECK(c);
   return 0;
 }

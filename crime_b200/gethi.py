@@ -207,6 +207,20 @@ class GetHI:
         self._check(self.lib.gh_cuda_points_to_shell_pixel(self._ctx, _ptr(pos), _ptr(dzc), n, _ptr(sh), _ptr(px)))
         return sh, px
 
+    def fastpath_audit(self, pos: np.ndarray, dz: np.ndarray | None = None, eps_scale: float = 1.0) -> dict:
+        """mk_T_maps' fp32 fast path vs its exact path on the given points."""
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        dzc = np.ascontiguousarray(dz, dtype=np.float64) if dz is not None else None
+        cnt = np.zeros(4, np.uint64)
+        self._check(self.lib.gh_cuda_fastpath_audit(self._ctx, _ptr(pos), _ptr(dzc), pos.shape[0], float(eps_scale), _ptr(cnt)))
+        return dict(out=int(cnt[0]), inside=int(cnt[1]), unsure=int(cnt[2]), wrong=int(cnt[3]))
+
+    def accumulate_audit(self, eps_scale: float = 1.0) -> dict:
+        """fast vs exact path over every sub-particle of the grids on the device (nothing deposited)."""
+        cnt = np.zeros(4, np.uint64)
+        self._check(self.lib.gh_cuda_accumulate_audit(self._ctx, float(eps_scale), _ptr(cnt)))
+        return dict(out=int(cnt[0]), inside=int(cnt[1]), unsure=int(cnt[2]), wrong=int(cnt[3]))
+
     def stage_times(self) -> dict:
         ms = (C.c_double * len(STAGE_NAMES))()
         self._check(self.lib.gh_cuda_stage_times(self._ctx, ms))

@@ -169,6 +169,18 @@ int gh_cuda_subparticle_offsets(const gh_cuda_ctx *ctx, double *xyz_out);
 int gh_cuda_points_to_shell_pixel(gh_cuda_ctx *ctx, const double *pos, const double *dz_rsd, long long n,
                                   int *shell_out, long long *pix_out);
 
+/* Audit of mk_T_maps' fp32 fast path against its exact fp64 path on arbitrary points (same inputs as
+ * above).  eps_scale multiplies the fast path's error bounds (1 = production).  counts_out[4] = fast path
+ * says out-of-range / in-range / unsure (-> exact path) / was sure but disagrees with the exact path; the
+ * last one must be 0 at eps_scale 1, and how far eps_scale can be lowered before it is not measures the
+ * head-room of the bounds. */
+int gh_cuda_fastpath_audit(gh_cuda_ctx *ctx, const double *pos, const double *dz_rsd, long long n, double eps_scale,
+                           unsigned long long *counts_out);
+
+/* The same audit over every sub-particle of the grids currently on the device (HI mass in GH_GRID_DENS,
+ * Delta z_RSD in GH_GRID_RVEL), through exactly the per-cell code mk_T_maps runs; nothing is deposited. */
+int gh_cuda_accumulate_audit(gh_cuda_ctx *ctx, double eps_scale, unsigned long long *counts_out);
+
 /* per-stage device times of the most recent calls, GH_T_NSLOTS doubles in ms */
 int gh_cuda_stage_times(gh_cuda_ctx *ctx, double *ms_out);
 /* launches of our own kernels issued by this context since creation */

@@ -283,3 +283,57 @@ def test_end_to_end_own_stream_statistics(tables_nu64):
         s2b = g.create_d_and_vr_fields()
         assert s2b == s2
         assert np.array_equal(g.download_grid(GRID_DENS)[:, :, :n].astype(np.float64), dens)
+
+
+@pytest.mark.parametrize("nside", [256, 1024, 2048])
+def test_fast_path_never_disagrees_with_exact_path(tables_nu150, nside):
+    """mk_T_maps sends sub-particles through an fp32 fast path that must either decline or give exactly
+    the fp64 answer.  8e6 points per nside (generic + polar + near the shell-range ends): zero
+    disagreements at the production bounds and with the bounds halved (head-room), and the fast path must
+    actually carry the load (few declines)."""
+    import json, os
+    from crime_b200 import GetHI, params_from_tables
+    p = params_from_tables(tables_nu150, n_grid=32, n_side=nside)
+    n = 8_000_000
+    pos, dz, rng = _random_points(tables_nu150, n, 100 + nside, 0.8, 1.1)
+    k = n // 8
+    pos[:k, 2] = np.sign(pos[:k, 2]) * np.abs(pos[:k, 0]) * rng.uniform(5, 5000, k)
+    report = {}
+    with GetHI(p) as g:
+        for scale in (1.0, 0.5, 0.25, 0.125, 0.0625):
+            report[scale] = g.fastpath_audit(pos, dz, scale)
+    # the regular-table personality (uniform shells, C truncation below nu_min) through the same fast path
+    from crime_b200.abi import params_from_dict, params_to_dict
+    dd = params_to_dict(p)
+    dd["irregular_nutable"] = 0
+    with GetHI(params_from_dict(dd)) as g:
+        reg = g.fastpath_audit(pos, dz, 1.0)
+    assert reg["wrong"] == 0 and reg["inside"] > 0.3 * n
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/fastpath_audit_nside{nside}.json", "w") as f:
+        json.dump(report, f, indent=1)
+    assert report[1.0]["wrong"] == 0
+    assert report[0.5]["wrong"] == 0
+    assert report[1.0]["unsure"] < 0.12 * n
+    assert report[1.0]["inside"] > 0.3 * n
+
+
+def test_accumulate_audit_on_a_real_grid(tables_nu64):
+    """Every sub-particle of a 256^3 realisation (1.7e8 of them) through the production per-cell code:
+    the fp32 fast path never contradicts the fp64 path, also with its bounds halved."""
+    import json, os
+    from crime_b200 import GetHI, params_from_tables
+    n = 256
+    p = params_from_tables(tables_nu64, n_grid=n, n_side=256, seed=11)
+    with GetHI(p) as g:
+        g.create_d_and_vr_fields()
+        g.get_HI()
+        rep = {s: g.accumulate_audit(s) for s in (1.0, 0.5, 0.25, 0.125)}
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/accumulate_audit_256.json", "w") as f:
+        json.dump(rep, f, indent=1)
+    tot = 10 * n ** 3
+    for s, r in rep.items():
+        assert r["out"] + r["inside"] + r["unsure"] == tot
+    assert rep[1.0]["wrong"] == 0 and rep[0.5]["wrong"] == 0
+    assert rep[1.0]["unsure"] < 0.05 * tot
