@@ -341,7 +341,7 @@ def test_accumulate_audit_on_a_real_grid(tables_nu64):
 
 def test_c_host_executable_end_to_end(tmp_path, oracle):
     """./GetHI <param_file> (the C host over the C-ABI): parameter file in, FITS shells + nuTable out; the maps
-    equal what the oracle computes from the same parameter block and the device's own k-space field."""
+    equal what the Python binding produces from the same parameter block (other tests tie that to the oracle)."""
     import subprocess
     from crime_b200 import GetHI, host
     from crime_b200.abi import params_from_dict
@@ -356,9 +356,7 @@ def test_c_host_executable_end_to_end(tmp_path, oracle):
     d = host.read_run_params(tmp_path / "p.ini")
     p = params_from_dict(d)
     with GetHI(p) as g:
-        g.generate_k()
-        dk, vk = g.download_delta_k()
-    ref = oracle.run(p, dk, vk)["maps"]
+        ref = g.run().copy()
     lines = (tmp_path / "run_nuTable.dat").read_text().splitlines()
     assert len(lines) == 16 and lines[0].split()[0] == "1"
     for s in range(16):
@@ -367,5 +365,4 @@ def test_c_host_executable_end_to_end(tmp_path, oracle):
         nz = ref[s] != 0
         assert np.array_equal(m != 0, nz)
         if nz.any():
-            # fields differ at the 1e-6 level between the fp32 device FFT and the oracle's, maps follow
-            assert np.abs(m[nz] / ref[s][nz] - 1).max() < 2e-3
+            assert np.abs(m[nz] / ref[s][nz] - 1).max() < 1e-5   # same device code; only the atomic order differs
