@@ -248,6 +248,13 @@ extern "C" int gh_cuda_create(const gh_cuda_params *p, int rank, int nranks, con
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; gh_set_error("cudaGetDeviceProperties failed"); return 1; }
   c->n_sm = prop.multiProcessorCount;
+  {
+    // y/x FFT plane batch: a third of L2 by default (GH_FFT_BATCH_MB overrides, 0 = whole slab per pass)
+    const char *e = getenv("GH_FFT_BATCH_MB");
+    const double mb = e ? atof(e) : (double)prop.l2CacheSize / 3.0 / (1024.0 * 1024.0);
+    c->fft_w_override = getenv("GH_FFT_W") ? atoi(getenv("GH_FFT_W")) : 0;
+    c->fft_batch_bytes = mb > 0 ? (size_t)(mb * 1024.0 * 1024.0) : (size_t)1 << 60;
+  }
 
   if (apply_params(c, p, rank, nranks)) { delete c; return 1; }
   GhDev &d = c->d;

@@ -162,6 +162,7 @@ struct StridedGeom {
   int tiles_per_group;
   long long src_group_stride, dst_group_stride;
   long long src_stride, dst_stride;  // element stride along the transformed axis
+  int grp0;                 // first group handled by this launch (plane batches)
   int blk_shift;            // source index n is split as (n >> blk_shift, n & mask): the received
   long long src_chunk;      // all-to-all blocks sit src_chunk apart (blk_shift = 30 disables the split)
 };
@@ -182,8 +183,9 @@ __global__ void __launch_bounds__(NT) fft_strided_kernel(const float2 *__restric
 {
   extern __shared__ float2 sm[];
   const int tile = blockIdx.x;
-  const int grp = tile / g.tiles_per_group;
-  const int l0 = (tile - grp * g.tiles_per_group) * W;
+  const int grp_rel = tile / g.tiles_per_group;
+  const int grp = g.grp0 + grp_rel;
+  const int l0 = (tile - grp_rel * g.tiles_per_group) * W;
   const float2 *sp = src + ((long long)grp * g.src_group_stride + l0);
   float2 *dp = dst + ((long long)grp * g.dst_group_stride + l0);
   const int nvalid = min(W, g.lines_per_group - l0);
@@ -280,17 +282,17 @@ __global__ void __launch_bounds__(NT) fft_c2r_rows_kernel(float2 *__restrict__ d
   }
 }
 
-template <int N> struct FftCfg {
-  static constexpr int W = (N <= 512) ? 16 : (N <= 2048 ? 8 : 4);       // strided tile width (lines)
+template <int N, int WSEL = 0> struct FftCfg {
+  static constexpr int W = WSEL ? WSEL : ((N <= 512) ? 16 : (N <= 2048 ? 8 : 4));  // strided tile width (lines)
   static constexpr int NT_S = (W * N / 16) < 64 ? 64 : ((W * N / 16) > 512 ? 512 : (W * N / 16));
   static constexpr int WR = (N <= 1024) ? 16 : (N <= 2048 ? 8 : 4);     // rows per tile of the x pass
   static constexpr int NT_R = (WR * (N / 2) / 16) < 64 ? 64 : ((WR * (N / 2) / 16) > 512 ? 512 : (WR * (N / 2) / 16));
 };
 
-template <int N>
+template <int N, int WSEL>
 int launch_strided(gh_cuda_ctx *c, const float2 *src, float2 *dst, const StridedGeom &g, int ngroups)
 {
-  using Cfg = FftCfg<N>;
+  using Cfg = FftCfg<N, WSEL>;
   auto kern = fft_strided_kernel<N, Cfg::W, Cfg::NT_S>;
   const size_t smem = (size_t)N * Cfg::W * sizeof(float2);
   GH_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -313,11 +315,11 @@ int launch_rows(gh_cuda_ctx *c, float2 *data, long long nrows, float norm)
   return 0;
 }
 
-template <int N>
+template <int N, int WSEL = 0>
 int fft_field(gh_cuda_ctx *c, float2 *field)
 {
   const GhDev &d = c->d;
-  using Cfg = FftCfg<N>;
+  using Cfg = FftCfg<N, WSEL>;
   const int nh = d.nh;
   const double normd = pow(sqrt(2.0 * 3.14159265358979323846) / d.l_box, 3.0);  // src/fourier.c:403
   // (1) z axis, local because k-space is ky-distributed: all nky_here*nh columns as one flat group
@@ -327,9 +329,10 @@ int fft_field(gh_cuda_ctx *c, float2 *field)
     g.tiles_per_group = (g.lines_per_group + Cfg::W - 1) / Cfg::W;
     g.src_group_stride = g.dst_group_stride = 0;
     g.src_stride = g.dst_stride = (long long)d.nky_here * nh;
+    g.grp0 = 0;
     g.blk_shift = 30;
     g.src_chunk = 0;
-    if (launch_strided<N>(c, field, field, g, 1)) return 1;
+    if (launch_strided<N, WSEL>(c, field, field, g, 1)) return 1;
   }
   const float2 *ysrc = field;
   StridedGeom g;
@@ -358,9 +361,19 @@ int fft_field(gh_cuda_ctx *c, float2 *field)
     g.blk_shift = 30;
     g.src_chunk = 0;
   }
-  // (3) y axis per z plane, (4) x axis half-complex -> real with the normalisation fused
-  if (launch_strided<N>(c, ysrc, field, g, d.nz_here)) return 1;
-  return launch_rows<N>(c, field, (long long)d.nz_here * d.n, (float)normd);
+  // (3) y axis per z plane, (4) x axis half-complex -> real with the normalisation fused.  The two passes
+  // run over batches of planes small enough to stay in the 126 MB L2, so the x pass finds the y pass's
+  // output there: HBM sees one read and one write per mode for both passes together.
+  const size_t plane_bytes = (size_t)d.n * nh * sizeof(float2);
+  const size_t nb_sz = c->fft_batch_bytes / plane_bytes;
+  const int nb = nb_sz < 1 ? 1 : (nb_sz > (size_t)d.nz_here ? d.nz_here : (int)nb_sz);
+  for (int z0 = 0; z0 < d.nz_here; z0 += nb) {
+    const int nz = (d.nz_here - z0 < nb) ? d.nz_here - z0 : nb;
+    g.grp0 = z0;
+    if (launch_strided<N, WSEL>(c, ysrc, field, g, nz)) return 1;
+    if (launch_rows<N>(c, field + (size_t)z0 * d.n * nh, (long long)nz * d.n, (float)normd)) return 1;
+  }
+  return 0;
 }
 
 }  // namespace
@@ -378,7 +391,7 @@ int gh_launch_fft_field(gh_cuda_ctx *c, float2 *field)
     case 128: return fft_field<128>(c, field);
     case 256: return fft_field<256>(c, field);
     case 512: return fft_field<512>(c, field);
-    case 1024: return fft_field<1024>(c, field);
+    case 1024: return (c->fft_w_override == 16) ? fft_field<1024, 16>(c, field) : fft_field<1024>(c, field);
     case 2048: return fft_field<2048>(c, field);
     case 4096: return fft_field<4096>(c, field);
     default:

@@ -5,12 +5,32 @@
 
 namespace {
 
+// Cell-centre coordinate along one axis, dx*(i+0.5) - pos_obs, in float without cancellation error:
+// the integer part of (0.5 - pos_obs/dx) is subtracted from the index exactly, the fraction rides on an fma.
+struct AxisF {
+  int ioff;
+  float dx, frac;
+  __device__ __forceinline__ float at(int i) const { return fmaf(dx, (float)(i - ioff), frac); }
+};
+__device__ __forceinline__ AxisF make_axis(double dx, double pos_obs, int i_origin)
+{
+  // x = dx*(i_local + i_origin + 0.5) - pos_obs = dx*((i_local - ioff) + f),  f in [0,1)
+  const double t = (double)i_origin + 0.5 - pos_obs / dx;
+  const double fl = floor(t);
+  AxisF a;
+  a.ioff = -(int)fl;
+  a.dx = (float)dx;
+  a.frac = (float)(dx * (t - fl));
+  return a;
+}
+
 // ------------------------------------------------------------------------------------------------
 // radial_velocity_from_potential (reference src/fourier.c:307-373): v = +grad(phi) by central
 // differences, periodic in x and y, neighbour planes in z come from the adjacent slabs
 // (src/fourier.c:415-428), projected on the line of sight from the observer.
-// One thread per cell, x fastest; the 6 neighbour loads hit L1/L2 (three planes of phi stay in the
-// 126 MB L2 while a plane is swept), so DRAM sees ~4 B read + 4 B written per cell.
+// Two cells per thread (rows are 8-byte aligned), x neighbours through warp shuffles, y/z neighbours as
+// float2 loads that hit L1/L2 (three planes of phi stay in the 126 MB L2 while a plane is swept), so
+// DRAM sees ~4 B read + 4 B written per cell.  One CTA = one row segment of 2*blockDim cells.
 __global__ void __launch_bounds__(256) radial_velocity_kernel(GhDev d, const float *__restrict__ vpot,
                                                               const float *__restrict__ plane_lo,
                                                               const float *__restrict__ plane_hi,
@@ -19,22 +39,40 @@ __global__ void __launch_bounds__(256) radial_velocity_kernel(GhDev d, const flo
   const int ngx = 2 * d.nh;
   const int iy = blockIdx.y, iz = blockIdx.z;
   const float hidx = (float)(0.5 / d.dx);
-  const float y = (float)(d.dx * (iy + 0.5) - d.pos_obs[1]);
-  const float z = (float)(d.dx * (iz + d.iz0 + 0.5) - d.pos_obs[2]);
+  const AxisF ax = make_axis(d.dx, d.pos_obs[0], 0), ay = make_axis(d.dx, d.pos_obs[1], 0), az = make_axis(d.dx, d.pos_obs[2], d.iz0);
+  const float y = ay.at(iy), z = az.at(iz);
   const int iy_hi = (iy == d.n - 1) ? 0 : iy + 1, iy_lo = (iy == 0) ? d.n - 1 : iy - 1;
   const size_t plane = (size_t)ngx * d.n;
   const float *p0 = vpot + (size_t)iz * plane;
-  const float *pz_lo = (iz == 0) ? plane_lo : p0 - plane;
-  const float *pz_hi = (iz == d.nz_here - 1) ? plane_hi : p0 + plane;
-  for (int ix = blockIdx.x * blockDim.x + threadIdx.x; ix < d.n; ix += gridDim.x * blockDim.x) {
-    const float x = (float)(d.dx * (ix + 0.5) - d.pos_obs[0]);
-    const int ix_hi = (ix == d.n - 1) ? 0 : ix + 1, ix_lo = (ix == 0) ? d.n - 1 : ix - 1;
-    const size_t row = (size_t)iy * ngx;
-    const float vx = hidx * (__ldg(p0 + row + ix_hi) - __ldg(p0 + row + ix_lo));
-    const float vy = hidx * (__ldg(p0 + (size_t)iy_hi * ngx + ix) - __ldg(p0 + (size_t)iy_lo * ngx + ix));
-    const float vz = hidx * (__ldg(pz_hi + row + ix) - __ldg(pz_lo + row + ix));
-    const float irr = rsqrtf(x * x + y * y + z * z);
-    rvel[(size_t)iz * plane + row + ix] = (vx * x + vy * y + vz * z) * irr;
+  const float *pz_lo = ((iz == 0) ? plane_lo : p0 - plane) + (size_t)iy * ngx;
+  const float *pz_hi = ((iz == d.nz_here - 1) ? plane_hi : p0 + plane) + (size_t)iy * ngx;
+  const float *row = p0 + (size_t)iy * ngx, *row_hi = p0 + (size_t)iy_hi * ngx, *row_lo = p0 + (size_t)iy_lo * ngx;
+  float *out = rvel + (size_t)iz * plane + (size_t)iy * ngx;
+  const int lane = threadIdx.x & 31;
+  const float yz2 = fmaf(y, y, z * z);
+  const int nper = d.n / 2;
+  // every lane of a warp runs the same number of iterations (the shuffles need the whole warp)
+  for (int base = blockIdx.x * blockDim.x; base < nper; base += gridDim.x * blockDim.x) {
+    const int ip = base + threadIdx.x;
+    const bool act = ip < nper;
+    const int ix = act ? 2 * ip : 0;
+    const float2 c = __ldg(reinterpret_cast<const float2 *>(row + ix));
+    const float2 yh = __ldg(reinterpret_cast<const float2 *>(row_hi + ix)), yl = __ldg(reinterpret_cast<const float2 *>(row_lo + ix));
+    const float2 zh = __ldg(reinterpret_cast<const float2 *>(pz_hi + ix)), zl = __ldg(reinterpret_cast<const float2 *>(pz_lo + ix));
+    // x neighbours: the left cell of my pair needs phi[ix-1] (previous lane's .y), the right one phi[ix+2]
+    float left = __shfl_up_sync(0xffffffffu, c.y, 1), right = __shfl_down_sync(0xffffffffu, c.x, 1);
+    if (lane == 0) left = __ldg(row + ((ix == 0) ? d.n - 1 : ix - 1));
+    if (lane == 31 || ip >= nper - 1) right = __ldg(row + ((ix + 2 >= d.n) ? 0 : ix + 2));
+    if (!act) continue;
+    const float x0 = ax.at(ix), x1 = ax.at(ix + 1);
+    const float vx0 = hidx * (c.y - left), vx1 = hidx * (right - c.x);
+    const float vy0 = hidx * (yh.x - yl.x), vy1 = hidx * (yh.y - yl.y);
+    const float vz0 = hidx * (zh.x - zl.x), vz1 = hidx * (zh.y - zl.y);
+    const float ir0 = rsqrtf(fmaf(x0, x0, yz2)), ir1 = rsqrtf(fmaf(x1, x1, yz2));
+    float2 r;
+    r.x = fmaf(vx0, x0, fmaf(vy0, y, vz0 * z)) * ir0;
+    r.y = fmaf(vx1, x1, fmaf(vy1, y, vz1 * z)) * ir1;
+    *reinterpret_cast<float2 *>(out + ix) = r;
   }
 }
 
@@ -113,10 +151,12 @@ __global__ void __launch_bounds__(256) get_HI_kernel(GhDev d, float *__restrict_
 {
   const int ngx = 2 * d.nh;
   const int iy = blockIdx.y, iz = blockIdx.z;
-  const float y = (float)(d.dx * (iy + 0.5) - d.pos_obs[1]);
-  const float z = (float)(d.dx * (iz + d.iz0 + 0.5) - d.pos_obs[2]);
-  const float mass_prefac = (float)(d.dx * d.dx * d.dx);
+  const AxisF ax = make_axis(d.dx, d.pos_obs[0], 0), ay = make_axis(d.dx, d.pos_obs[1], 0), az = make_axis(d.dx, d.pos_obs[2], d.iz0);
+  const float y = ay.at(iy), z = az.at(iz);
+  const float yz2 = fmaf(y, y, z * z);
+  const float mass_prefac = (float)(d.dx * d.dx * d.dx) * 0.008f;  // dx^3 * x_HI amplitude (src/user_defined.c:27-30)
   const float idr = (float)d.glob_idr, rmax = (float)d.r_tab_max;
+  const float half_s2 = 0.5f * sigma2_gauss;
   const size_t base = ((size_t)iz * d.n + iy) * ngx;
   const int last = d.nz_tab - 1;
   // two cells per thread: rows are 8-byte aligned
@@ -126,25 +166,22 @@ __global__ void __launch_bounds__(256) get_HI_kernel(GhDev d, float *__restrict_
     float dd[2] = {dv.x, dv.y}, rv[2] = {vv.x, vv.y};
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      const float x = (float)(d.dx * (2 * ip + j + 0.5) - d.pos_obs[0]);
-      const float r = sqrtf(x * x + y * y + z * z);
-      float redshift, gd, gv;
-      if (r <= 0.f) { redshift = 0.f; gd = 1.f; gv = 1.f; }
-      else if (r >= rmax) { redshift = __ldg(d.z_r2z_f + last); gd = __ldg(d.gd_f + last); gv = __ldg(d.gv_f + last); }
-      else {
-        const float s = r * idr;
-        int ir = (int)s;
-        if (ir > last - 1) ir = last - 1;
-        const float t = s - (float)ir;
-        redshift = lerp_tab(d.z_r2z_f, ir, t);
-        gd = lerp_tab(d.gd_f, ir, t);
-        gv = lerp_tab(d.gv_f, ir, t);
-      }
-      const float opz = 1.f + redshift;
-      const float gfd = gd * (0.904f + 0.135f * powf(opz, 1.696f));                  // D(r) * b_HI(z)
-      const float dens_ln = expf(gfd * (dd[j] - 0.5f * gfd * sigma2_gauss));         // lognormal
-      dd[j] = mass_prefac * (0.008f * powf(opz, 0.6f)) * dens_ln;                    // dx^3 x_HI(z) rho_LN
-      rv[j] = rv[j] * gv;                                                            // Delta z_RSD
+      const float x = ax.at(2 * ip + j);
+      const float r2 = fmaf(x, x, yz2);
+      const float r = r2 * rsqrtf(fmaxf(r2, 1e-30f));
+      // z_of_r / dgrowth_of_r / vgrowth_of_r: same bin, same weight (src/cosmo.c:52-86); r=0 and the clamp
+      // beyond the table fall out of the arithmetic (tables start at (0,1,1))
+      const float s = fminf(r, rmax) * idr;
+      const int ir = min((int)s, last - 1);
+      const float t = s - (float)ir;
+      const float redshift = lerp_tab(d.z_r2z_f, ir, t);
+      const float gd = lerp_tab(d.gd_f, ir, t);
+      const float gv = lerp_tab(d.gv_f, ir, t);
+      const float l2 = __log2f(1.f + redshift);
+      const float gfd = gd * fmaf(0.135f, exp2f(1.696f * l2), 0.904f);                        // D(r) * b_HI(z)
+      const float dens_ln = exp2f(1.4426950408889634f * (gfd * fmaf(-half_s2, gfd, dd[j])));  // exp(gfd (d - gfd s2/2))
+      dd[j] = mass_prefac * exp2f(0.6f * l2) * dens_ln;                                       // dx^3 x_HI(z) rho_LN
+      rv[j] = rv[j] * gv;                                                                     // Delta z_RSD
     }
     *reinterpret_cast<float2 *>(dens + base + 2 * ip) = make_float2(dd[0], dd[1]);
     *reinterpret_cast<float2 *>(rvel + base + 2 * ip) = make_float2(rv[0], rv[1]);
@@ -174,7 +211,7 @@ int gh_launch_radial_velocity(gh_cuda_ctx *c)
     lo = vpot + (size_t)(d.n - 1) * plane;  // src/fourier.c:425-427
     hi = vpot;
   }
-  dim3 grid((d.n + 255) / 256, d.n, d.nz_here);
+  dim3 grid((d.n / 2 + 255) / 256, d.n, d.nz_here);
   radial_velocity_kernel<<<grid, 256, 0, c->stream>>>(d, vpot, lo, hi, reinterpret_cast<float *>(c->gridC));
   GH_LAUNCH_CHECK(c);
   return 0;

@@ -63,6 +63,8 @@ struct gh_cuda_ctx {
   bool ev_used[GH_T_NSLOTS];
   unsigned long long launches;
   int n_sm;
+  int fft_w_override;      // experiment knob: strided tile width for N=1024
+  size_t fft_batch_bytes;  // plane batch of the fused y/x FFT passes (kept L2-resident)
 };
 
 void gh_set_error(const char *fmt, ...);

@@ -3,21 +3,22 @@
 // Replaces create_density_and_velpot_fourier (reference src/fourier.c:234-305), pk_linear0
 // (src/cosmo.c:153-170) and rng_delta_gauss (src/common.c:154-164).  The reference draws from one
 // MT19937 per OpenMP thread, so its realisation depends on the thread and rank count; here every mode
-// draws from Philox4x32-10 keyed on (seed, GLOBAL mode index kx + nh*(ky + n*kz)) -- the reference's own
+// draws from Philox4x32-10 keyed on (seed, GLOBAL mode index g = kx + nh*(ky + n*kz)) -- the reference's own
 // single-process index (src/fourier.c:278) -- so the field is identical for any number of GPUs.
-//   counter = (index lo, index hi, 0, 0), key = (seed, 'GetH');
-//   u1 = (out[0] >> 8) * 2^-24  -> phase = 2 pi u1;   u2 = (out[1] >> 8) * 2^-24 -> |delta| = sqrt(-sigma2 ln(1-u2))
-// P(k): bin index and interpolation in double from shared memory (a float log10 would flip bins at
-// table nodes, where the reference's interpolant is discontinuous); Rayleigh/phase maths in float.
+//   counter = (g>>1 lo, g>>1 hi, 0, 0), key = (seed, 'GetH'); the even mode of a pair takes words 0,1 and the
+//   odd one words 2,3:  u1 = (w_a >> 8) * 2^-24 -> phase = 2 pi u1;  u2 = (w_b >> 8) * 2^-24 -> |delta| =
+//   sqrt(-sigma2 ln(1-u2)).  One thread owns one pair, so one Philox block serves two modes.
+// P(k): the reference indexes its table with (int)((0.5 log10 k^2 - logkmin) * idlogk) in double.  Here the
+// bin comes from a float log2; only when that lands within 2e-3 of a bin boundary (where the reference's
+// interpolant is discontinuous, so the bin matters) is the double expression evaluated.
 // Layout written: [kz][ky_local][kx], ky_local in this rank's ky slab -- ready for a local z transform.
-// Write-only, 16 B/mode (two complex-float fields): each thread produces two adjacent modes and stores
-// one float4 per field.
+// Write-only, 16 B/mode (two complex-float fields), coalesced 8-byte stores.
 #include "gh_internal.cuh"
 
 namespace {
 
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1, uint32_t &o0,
-                                              uint32_t &o1)
+                                              uint32_t &o1, uint32_t &o2, uint32_t &o3)
 {
   uint32_t c2 = 0u, c3 = 0u;
 #pragma unroll
@@ -28,73 +29,94 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
-  o0 = c0; o1 = c1;
+  o0 = c0; o1 = c1; o2 = c2; o3 = c3;
 }
 
-__device__ __forceinline__ double signed_k(int i, int n, double dk) { return (2 * i <= n) ? i * dk : -(n - i) * dk; }
+__device__ __forceinline__ int signed_idx(int i, int n) { return (2 * i <= n) ? i : i - n; }
 
-// src/cosmo.c:153-170
-__device__ __forceinline__ double pk_linear0(const GhDev &d, const double *s_logk, const double *s_pk, double lgk)
+// src/cosmo.c:153-170 with the bin chosen in float (double only next to a bin boundary)
+__device__ __forceinline__ float pk_lookup(const GhDev &d, const double *s_logk, const double *s_pk, const float *s_logk_f,
+                                           const float *s_pk_f, float k2f, double k2)
 {
-  const int ik = (int)((lgk - d.logkmin) * d.idlogk);
-  if (ik < 0) return s_pk[0] * pow(10.0, d.n_scal * (lgk - d.logkmin));
-  if (ik < d.numk) {
-    const double hi = (ik + 1 < d.numk) ? s_pk[ik + 1] : s_pk[ik];
-    return s_pk[ik] + (lgk - s_logk[ik]) * (hi - s_pk[ik]) * d.idlogk;
+  // lgk = 0.5 log10(k2)
+  const float lgk = 0.15051499783199059761f * __log2f(k2f);  // 0.5*log10(2)*log2
+  const float xf = (lgk - (float)d.logkmin) * (float)d.idlogk;
+  int ik = (int)floorf(xf);
+  const float fr = xf - (float)ik;
+  if (fr < 2e-3f || fr > 1.0f - 2e-3f || ik < 1 || ik >= d.numk - 2) {
+    // rare: decide the bin (and the two extrapolation branches) exactly as the reference does
+    const double lg = 0.5 * log10(k2);
+    const int ikd = (int)((lg - d.logkmin) * d.idlogk);
+    if (ikd < 0) return (float)(s_pk[0] * pow(10.0, d.n_scal * (lg - d.logkmin)));
+    if (ikd >= d.numk) return (float)(s_pk[d.numk - 1] * pow(10.0, -3.0 * (lg - d.logkmax)));
+    const double hi = (ikd + 1 < d.numk) ? s_pk[ikd + 1] : s_pk[ikd];
+    return (float)(s_pk[ikd] + (lg - s_logk[ikd]) * (hi - s_pk[ikd]) * d.idlogk);
   }
-  return s_pk[d.numk - 1] * pow(10.0, -3.0 * (lgk - d.logkmax));
+  const float a = s_pk_f[ik], b = s_pk_f[ik + 1];
+  return fmaf((lgk - s_logk_f[ik]) * (float)d.idlogk, b - a, a);
 }
 
-__device__ __forceinline__ void one_mode(const GhDev &d, const double *s_logk, const double *s_pk, long long local,
+__device__ __forceinline__ void one_mode(const GhDev &d, const double *s_logk, const double *s_pk, const float *s_logk_f,
+                                         const float *s_pk_f, int kx, int ky, int kz, uint32_t wa, uint32_t wb,
                                          float2 &dk_out, float2 &vk_out)
 {
-  // local index -> (kz, ky_local, kx) of the [kz][ky_local][kx] slab
-  const int kx = (int)(local % d.nh);
-  const long long t = local / d.nh;
-  const int kyl = (int)(t % d.nky_here), kz = (int)(t / d.nky_here);
-  const int ky = d.ky0 + kyl;
-  const double fx = signed_k(kx, d.n, d.dk), fy = signed_k(ky, d.n, d.dk), fz = signed_k(kz, d.n, d.dk);
-  const double k2 = fx * fx + fy * fy + fz * fz;
-  if (k2 <= 0.0) {  // src/fourier.c:287-290
+  const int ix = signed_idx(kx, d.n), iy = signed_idx(ky, d.n), iz = signed_idx(kz, d.n);
+  const int m2 = ix * ix + iy * iy + iz * iz;  // <= 3 (n/2)^2 < 2^24: exact in float
+  if (m2 == 0) {  // src/fourier.c:287-290
     dk_out = make_float2(0.f, 0.f);
     vk_out = make_float2(0.f, 0.f);
     return;
   }
-  const unsigned long long gidx = (unsigned long long)kx + (unsigned long long)d.nh * ((unsigned long long)ky + (unsigned long long)d.n * kz);
-  uint32_t r0, r1;
-  philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), d.seed, 0x47657448u, r0, r1);
-  const float u1 = (float)(r0 >> 8) * 5.9604644775390625e-8f;  // 2^-24
-  const float u2 = (float)(r1 >> 8) * 5.9604644775390625e-8f;
-  const double lgk = 0.5 * log10(k2);
-  double sigma2 = pk_linear0(d, s_logk, s_pk, lgk) * d.idk3;
-  float s2f = (float)sigma2;
+  const double k2 = d.dk * d.dk * (double)m2;
   const float k2f = (float)k2;
-  if (d.do_smoothing) s2f *= expf(-(float)d.r2_smooth * k2f);  // src/fourier.c:294-295
-  const float mod = sqrtf(-s2f * log1pf(-u2));                 // src/common.c:163
+  const float u1 = (float)(wa >> 8) * 5.9604644775390625e-8f;  // 2^-24
+  const float u2 = (float)(wb >> 8) * 5.9604644775390625e-8f;
+  float s2f = pk_lookup(d, s_logk, s_pk, s_logk_f, s_pk_f, k2f, k2) * (float)d.idk3;
+  if (d.do_smoothing) s2f *= __expf(-(float)d.r2_smooth * k2f);   // src/fourier.c:294-295
+  const float mod = sqrtf(-s2f * log1pf(-u2));                     // src/common.c:163
   float sn, cs;
-  sincospif(2.0f * u1, &sn, &cs);                              // phase = 2 pi u1, src/common.c:161
+  sincospif(2.0f * u1, &sn, &cs);                                  // phase = 2 pi u1, src/common.c:161
   dk_out = make_float2(mod * cs, mod * sn);
-  const float vf = (float)d.vfactor / k2f;                     // f0*H0/k^2, src/fourier.c:298
+  const float vf = __fdividef((float)d.vfactor, k2f);              // f0*H0/k^2, src/fourier.c:298
   vk_out = make_float2(dk_out.x * vf, dk_out.y * vf);
 }
 
-__global__ void __launch_bounds__(256) kgen_kernel(GhDev d, float2 *__restrict__ dens_k, float2 *__restrict__ vpot_k,
-                                                   long long npairs)
+__global__ void __launch_bounds__(256) kgen_kernel(GhDev d, float2 *__restrict__ dens_k, float2 *__restrict__ vpot_k)
 {
   extern __shared__ double s_tab[];
   double *s_logk = s_tab, *s_pk = s_tab + d.numk;
+  float *s_logk_f = reinterpret_cast<float *>(s_tab + 2 * d.numk), *s_pk_f = s_logk_f + d.numk;
   for (int i = threadIdx.x; i < d.numk; i += blockDim.x) {
-    s_logk[i] = d.logkarr[i];
-    s_pk[i] = d.pkarr[i];
+    const double a = d.logkarr[i], b = d.pkarr[i];
+    s_logk[i] = a; s_pk[i] = b;
+    s_logk_f[i] = (float)a; s_pk_f[i] = (float)b;
   }
   __syncthreads();
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long pair = (long long)blockIdx.x * blockDim.x + threadIdx.x; pair < npairs; pair += stride) {
-    float2 a0, v0, a1, v1;
-    one_mode(d, s_logk, s_pk, 2 * pair, a0, v0);
-    one_mode(d, s_logk, s_pk, 2 * pair + 1, a1, v1);
-    reinterpret_cast<float4 *>(dens_k)[pair] = make_float4(a0.x, a0.y, a1.x, a1.y);
-    reinterpret_cast<float4 *>(vpot_k)[pair] = make_float4(v0.x, v0.y, v1.x, v1.y);
+  const int kz = blockIdx.y;
+  const unsigned plane_len = (unsigned)d.nky_here * (unsigned)d.nh;                       // modes of this plane here
+  const unsigned long long gb = (unsigned long long)d.nh * ((unsigned long long)d.ky0 + (unsigned long long)d.n * kz);
+  const unsigned long long q0 = gb >> 1;
+  const unsigned npairs = (unsigned)(((gb + plane_len + 1) >> 1) - q0);
+  const float inv_nh = 1.0f / (float)d.nh;
+  float2 *dplane = dens_k + (size_t)kz * plane_len, *vplane = vpot_k + (size_t)kz * plane_len;
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < npairs; t += gridDim.x * blockDim.x) {
+    const unsigned long long q = q0 + t;
+    uint32_t w0, w1, w2, w3;
+    philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), d.seed, 0x47657448u, w0, w1, w2, w3);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const long long off = (long long)(2 * q + s) - (long long)gb;
+      if (off < 0 || off >= (long long)plane_len) continue;
+      const unsigned loc = (unsigned)off;
+      int kyl = (int)((float)loc * inv_nh);
+      int kx = (int)loc - kyl * d.nh;
+      if (kx < 0) { kyl--; kx += d.nh; }
+      else if (kx >= d.nh) { kyl++; kx -= d.nh; }
+      float2 a, v;
+      one_mode(d, s_logk, s_pk, s_logk_f, s_pk_f, kx, d.ky0 + kyl, kz, s ? w2 : w0, s ? w3 : w1, a, v);
+      dplane[loc] = a;
+      vplane[loc] = v;
+    }
   }
 }
 
@@ -103,18 +125,17 @@ __global__ void __launch_bounds__(256) kgen_kernel(GhDev d, float2 *__restrict__
 int gh_launch_kgen(gh_cuda_ctx *c)
 {
   const GhDev &d = c->d;
-  const long long nmodes = (long long)d.n * d.nky_here * d.nh;  // even: n is even
-  const long long npairs = nmodes / 2;
-  const size_t smem = 2 * sizeof(double) * (size_t)d.numk;
+  const size_t smem = (2 * sizeof(double) + 2 * sizeof(float)) * (size_t)d.numk;
   if (smem > 200 * 1024) {
     gh_set_error("P(k) table with %d rows does not fit in shared memory", d.numk);
     return 1;
   }
   GH_CUDA_OK(cudaFuncSetAttribute(kgen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  long long blocks = (npairs + 255) / 256;
-  const long long cap = (long long)c->n_sm * 8;  // grid-stride over a whole number of waves
-  if (blocks > cap) blocks = cap;
-  kgen_kernel<<<(unsigned)blocks, 256, smem, c->stream>>>(d, c->gridA, c->gridB, npairs);
+  const unsigned pairs = ((unsigned)d.nky_here * (unsigned)d.nh + 3) / 2;
+  unsigned bx = (pairs + 255) / 256;
+  if (bx > 8) bx = 8;  // few, fat CTAs per plane amortise the 13 KB table load; the n planes supply the parallelism
+  dim3 grid(bx, d.n);
+  kgen_kernel<<<grid, 256, smem, c->stream>>>(d, c->gridA, c->gridB);
   GH_LAUNCH_CHECK(c);
   return 0;
 }

@@ -113,8 +113,8 @@ void oracle_philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], ui
   memcpy(out, c, sizeof(c));
 }
 
-/* Product stream: counter = (global mode index lo, hi, 0, 0), key = (seed, 'GetH'); u1 = (out[0]>>8)/2^24
- * (phase), u2 = (out[1]>>8)/2^24 (modulus) -- 24-bit uniforms, exact in float, u2 < 1 so ln(1-u2) is finite.  The global mode index is the reference's single-process index
+/* Product stream: counter = (g>>1 lo, g>>1 hi, 0, 0) for global mode index g, key = (seed, 'GetH'); the even
+ * mode of a pair uses words 0,1 and the odd one words 2,3: u1 = (w_a>>8)/2^24 (phase), u2 = (w_b>>8)/2^24 (modulus) -- 24-bit uniforms, exact in float, u2 < 1 so ln(1-u2) is finite.  The global mode index is the reference's single-process index
  * kk + nh*(jj + n*ii) (fourier.c:278), so the realisation does not depend on the number of GPUs.
  * Rows ky in [ky0, ky0+nky).  transposed_layout=0: reference layout restricted to those rows,
  * out[(kz*nky + (ky-ky0))*nh + kx] -- for nky==n this is exactly [kz][ky][kx]. */
@@ -135,8 +135,11 @@ void oracle_kgen_philox(const gh_cuda_params *p, int ky0, int nky, float _Comple
         double kx = signed_wavenumber(kk, n, dk);
         double k2 = kx * kx + ky * ky + kz * kz;
         uint64_t gidx = (uint64_t)kk + (uint64_t)nh * ((uint64_t)jj + (uint64_t)n * ii);
-        uint32_t ctr[4] = {(uint32_t)gidx, (uint32_t)(gidx >> 32), 0, 0}, r[4];
-        oracle_philox4x32_10(ctr, key, r);
+        uint64_t blk = gidx >> 1; /* one Philox block serves the two modes of a pair */
+        uint32_t ctr[4] = {(uint32_t)blk, (uint32_t)(blk >> 32), 0, 0}, r4[4], r[2];
+        oracle_philox4x32_10(ctr, key, r4);
+        r[0] = r4[2 * (gidx & 1)];
+        r[1] = r4[2 * (gidx & 1) + 1];
         size_t o = ((size_t)ii * nky + jl) * nh + kk;
         mode_from_uniforms(p, k2, idk3, factor, (r[0] >> 8) / 16777216.0, (r[1] >> 8) / 16777216.0, &dens_k[o], &vpot_k[o]);
       }
