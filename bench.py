@@ -237,13 +237,15 @@ def main():
     stream = torch.cuda.ExternalStream(g.stream_handle(), device=dev)
     cells = float(n_grid) ** 3
 
-    def timed(fn, steps):
+    def timed(fn, steps, finish=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(stream)
-        for _ in range(steps):
-            fn()
+        for i in range(steps):
+            fn(i)
+        if finish is not None:
+            finish()
         e1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
@@ -252,12 +254,15 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), wall
 
-    def step_resident():
+    def step_resident(i=0):
         g.run(to_host=False)
 
-    def step_e2e():
-        g.set_params(params)       # host -> device: the run's parameter block and tables
-        g.run(to_host=True)        # device -> host: this rank's finished maps (pinned)
+    def step_e2e(i=0):
+        # host -> device: the run's parameter block and tables; device -> host: this rank's finished maps into
+        # one of two pinned buffers.  Nothing waits for the copy until the end (gh_cuda_run_async /
+        # gh_cuda_wait): the copy of realisation i overlaps the computation of realisation i+1.
+        g.set_params(params)
+        g.run_async(i & 1)
 
     for _ in range(args.warmup):
         step_resident()
@@ -266,9 +271,11 @@ def main():
     l0 = g.kernel_launches()
     ms_res, _ = timed(step_resident, args.steps)
     launches = g.kernel_launches() - l0
-    for _ in range(2):
-        step_e2e()
-    ms_e2e, wall_e2e = timed(step_e2e, args.steps)
+    for i in range(2):
+        step_e2e(i)
+    g.wait()
+    ms_e2e, wall_e2e = timed(step_e2e, args.steps, finish=g.wait)
+    g.run(to_host=True)  # one synchronous realisation so that the per-stage timers below include an unoverlapped copy
     clocks = sampler.stop()
     stage_ms = g.stage_times()
 

@@ -210,6 +210,10 @@ extern "C" int gh_cuda_destroy(gh_cuda_ctx *c)
   cudaFree(c->twiddle); cudaFree(c->d_partials); cudaFree(c->d_prefac); cudaFree(c->d_tables);
   for (int i = 0; i < 2 * GH_T_NSLOTS; ++i)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  if (c->ev_done) cudaEventDestroy(c->ev_done);
+  if (c->ev_copied) cudaEventDestroy(c->ev_copied);
+  if (c->h_stats) cudaFreeHost(c->h_stats);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -249,9 +253,9 @@ extern "C" int gh_cuda_create(const gh_cuda_params *p, int rank, int nranks, con
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; gh_set_error("cudaGetDeviceProperties failed"); return 1; }
   c->n_sm = prop.multiProcessorCount;
   {
-    // y/x FFT plane batch: a third of L2 by default (GH_FFT_BATCH_MB overrides, 0 = whole slab per pass)
+    // y/x FFT plane batch in MB (GH_FFT_BATCH_MB; 0 / unset = whole slab per pass)
     const char *e = getenv("GH_FFT_BATCH_MB");
-    const double mb = e ? atof(e) : (double)prop.l2CacheSize / 3.0 / (1024.0 * 1024.0);
+    const double mb = e ? atof(e) : 0.0;  // measured: batching through L2 does not pay on B200 (profiles/), off by default
     c->fft_w_override = getenv("GH_FFT_W") ? atoi(getenv("GH_FFT_W")) : 0;
     c->fft_batch_bytes = mb > 0 ? (size_t)(mb * 1024.0 * 1024.0) : (size_t)1 << 60;
   }
@@ -271,6 +275,10 @@ extern "C" int gh_cuda_create(const gh_cuda_params *p, int rank, int nranks, con
   } while (0)
 
   CREATE_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CREATE_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CREATE_OK(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+  CREATE_OK(cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming));
+  CREATE_OK(cudaMallocHost((void **)&c->h_stats, 4 * sizeof(double)));
   for (int i = 0; i < 2 * GH_T_NSLOTS; ++i) CREATE_OK(cudaEventCreate(&c->ev[i]));
   if (upload_tables(c, p)) { gh_cuda_destroy(c); return 1; }
 
@@ -288,7 +296,7 @@ extern "C" int gh_cuda_create(const gh_cuda_params *p, int rank, int nranks, con
     CREATE_OK(cudaMalloc(&c->halo_hi, plane_bytes));
     CREATE_OK(cudaMalloc(&c->maps_recv, (size_t)shells_per_rank * d.npix * sizeof(float)));
   }
-  CREATE_OK(cudaMalloc(&c->d_partials, sizeof(double) * (2 + 2 * (size_t)c->n_sm * 8)));
+  CREATE_OK(cudaMalloc(&c->d_partials, sizeof(double) * (8 + 2 * (size_t)c->n_sm * 8)));
   CREATE_OK(cudaMalloc(&c->d_prefac, sizeof(double) * d.n_nu_pad));
   CREATE_OK(cudaMemcpyAsync(c->d_prefac, c->h_prefac, sizeof(double) * d.n_nu_pad, cudaMemcpyHostToDevice, c->stream));
   {
@@ -410,23 +418,31 @@ extern "C" int gh_cuda_radial_velocity(gh_cuda_ctx *c)
   return gh_launch_radial_velocity(c);
 }
 
+// variance chain, all on the device: per-CTA partials -> sums -> (all-reduce) -> mean / sigma2 in d_partials[4..5];
+// the four numbers are also copied to pinned host memory for whoever asks later
+static int enqueue_sigma(gh_cuda_ctx *c)
+{
+  StageTimer t(c, GH_T_SIGMA);
+  if (gh_launch_sigma(c)) return 1;
+  if (c->d.nranks > 1) GH_NCCL_OK(ncclAllReduce(c->d_partials, c->d_partials, 2, ncclDouble, ncclSum, c->comm, c->stream));
+  if (gh_launch_sigma_finish(c)) return 1;
+  GH_CUDA_OK(cudaMemcpyAsync(c->h_stats, c->d_partials, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  GH_CUDA_OK(cudaMemcpyAsync(c->h_stats + 2, c->d_partials + 4, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (c->sigma_overridden)  // a caller-supplied sigma2_gauss wins over the measured one
+    GH_CUDA_OK(cudaMemcpyAsync(c->d_partials + 5, &c->sigma2_gauss, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  c->sigma_ready = true;
+  return 0;
+}
+
 extern "C" int gh_cuda_sigma_dens(gh_cuda_ctx *c, double *sigma2_out, double *mean_out)
 {
   GH_CTX(c);
-  double sums[2];
-  {
-    StageTimer t(c, GH_T_SIGMA);
-    if (gh_launch_sigma(c)) return 1;
-    if (c->d.nranks > 1) GH_NCCL_OK(ncclAllReduce(c->d_partials, c->d_partials, 2, ncclDouble, ncclSum, c->comm, c->stream));
-  }
-  GH_CUDA_OK(cudaMemcpyAsync(sums, c->d_partials, sizeof(sums), cudaMemcpyDeviceToHost, c->stream));
+  if (enqueue_sigma(c)) return 1;
   GH_CUDA_OK(cudaStreamSynchronize(c->stream));
-  const double ng_tot = (double)c->d.n * ((double)c->d.n * (double)c->d.n);
-  const double mean = sums[0] / ng_tot;  // src/fourier.c:59-60,74
-  c->mean_gauss = mean;
-  if (!c->sigma_overridden) c->sigma2_gauss = sums[1] / ng_tot - mean * mean;
-  if (sigma2_out) *sigma2_out = sums[1] / ng_tot - mean * mean;
-  if (mean_out) *mean_out = mean;
+  c->mean_gauss = c->h_stats[2];
+  if (!c->sigma_overridden) c->sigma2_gauss = c->h_stats[3];
+  if (sigma2_out) *sigma2_out = c->h_stats[3];
+  if (mean_out) *mean_out = c->h_stats[2];
   return 0;
 }
 
@@ -442,7 +458,7 @@ extern "C" int gh_cuda_create_d_and_vr_fields(gh_cuda_ctx *c, double *sigma2_out
 extern "C" int gh_cuda_get_HI(gh_cuda_ctx *c)
 {
   GH_CTX(c);
-  GH_REQUIRE(c->sigma2_gauss >= 0, "gh_cuda_get_HI: sigma2_gauss not set (run create_d_and_vr_fields or set it)");
+  GH_REQUIRE(c->sigma_ready, "gh_cuda_get_HI: sigma2_gauss not set (run create_d_and_vr_fields or set it)");
   StageTimer t(c, GH_T_GETHI);
   return gh_launch_get_HI(c);
 }
@@ -450,6 +466,8 @@ extern "C" int gh_cuda_get_HI(gh_cuda_ctx *c)
 extern "C" int gh_cuda_zero_maps(gh_cuda_ctx *c)
 {
   GH_CTX(c);
+  // a device->host copy of the previous realisation's maps may still be reading them
+  if (c->copy_pending) GH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_copied, 0));
   GH_CUDA_OK(cudaMemsetAsync(c->maps, 0, (size_t)c->d.n_nu_pad * c->d.npix * sizeof(float), c->stream));
   return 0;
 }
@@ -461,9 +479,9 @@ extern "C" int gh_cuda_accumulate_maps(gh_cuda_ctx *c)
   return gh_launch_accumulate(c);
 }
 
-extern "C" int gh_cuda_mk_T_maps(gh_cuda_ctx *c, float *maps_host)
+// accumulate -> (reduce-scatter) -> scale -> device->host copy on the copy stream; no host synchronisation
+static int enqueue_maps(gh_cuda_ctx *c, float *maps_host)
 {
-  GH_CTX(c);
   const GhDev &d = c->d;
   int n_here = 0, s0 = 0;
   gh_cuda_shells(c, &n_here, &s0);
@@ -490,18 +508,54 @@ extern "C" int gh_cuda_mk_T_maps(gh_cuda_ctx *c, float *maps_host)
     result = c->maps_recv;
   }
   if (maps_host && n_here > 0) {
-    StageTimer t(c, GH_T_D2H);
-    GH_CUDA_OK(cudaMemcpyAsync(maps_host, result, (size_t)n_here * d.npix * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    GH_CUDA_OK(cudaEventRecord(c->ev_done, c->stream));
+    GH_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_done, 0));
+    GH_CUDA_OK(cudaEventRecord(c->ev[2 * GH_T_D2H], c->copy_stream));
+    GH_CUDA_OK(cudaMemcpyAsync(maps_host, result, (size_t)n_here * d.npix * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+    GH_CUDA_OK(cudaEventRecord(c->ev[2 * GH_T_D2H + 1], c->copy_stream));
+    c->ev_used[GH_T_D2H] = true;
+    GH_CUDA_OK(cudaEventRecord(c->ev_copied, c->copy_stream));
+    c->copy_pending = true;
   }
-  GH_CUDA_OK(cudaStreamSynchronize(c->stream));
   return 0;
+}
+
+extern "C" int gh_cuda_wait(gh_cuda_ctx *c, double *sigma2_out)
+{
+  GH_CTX(c);
+  GH_CUDA_OK(cudaStreamSynchronize(c->stream));
+  if (c->copy_pending) GH_CUDA_OK(cudaEventSynchronize(c->ev_copied));
+  c->copy_pending = false;
+  if (c->sigma_ready) {
+    c->mean_gauss = c->h_stats[2];
+    if (!c->sigma_overridden) c->sigma2_gauss = c->h_stats[3];
+    if (sigma2_out) *sigma2_out = c->h_stats[3];
+  }
+  return 0;
+}
+
+extern "C" int gh_cuda_mk_T_maps(gh_cuda_ctx *c, float *maps_host)
+{
+  GH_CTX(c);
+  if (enqueue_maps(c, maps_host)) return 1;
+  return gh_cuda_wait(c, nullptr);
+}
+
+extern "C" int gh_cuda_run_async(gh_cuda_ctx *c, float *maps_host)
+{
+  GH_CTX(c);
+  if (!c->k_injected && gh_cuda_generate_k(c)) return 1;
+  if (gh_cuda_fft_fields(c)) return 1;
+  if (gh_cuda_radial_velocity(c)) return 1;
+  if (enqueue_sigma(c)) return 1;
+  if (gh_cuda_get_HI(c)) return 1;
+  return enqueue_maps(c, maps_host);
 }
 
 extern "C" int gh_cuda_run(gh_cuda_ctx *c, double *sigma2_out, float *maps_host)
 {
-  if (gh_cuda_create_d_and_vr_fields(c, sigma2_out, nullptr)) return 1;
-  if (gh_cuda_get_HI(c)) return 1;
-  return gh_cuda_mk_T_maps(c, maps_host);
+  if (gh_cuda_run_async(c, maps_host)) return 1;
+  return gh_cuda_wait(c, sigma2_out);
 }
 
 // ------------------------------------------------------------------------------------------------ injection / read-back
@@ -569,6 +623,10 @@ extern "C" int gh_cuda_set_sigma2_gauss(gh_cuda_ctx *c, double sigma2)
   GH_REQUIRE(c, "null gh_cuda context");
   c->sigma2_gauss = sigma2;
   c->sigma_overridden = true;
+  c->sigma_ready = true;
+  GH_CUDA_OK(cudaSetDevice(c->device));
+  GH_CUDA_OK(cudaMemcpyAsync(c->d_partials + 5, &c->sigma2_gauss, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  GH_CUDA_OK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 

@@ -17,8 +17,10 @@
 //                        layout, transformed in place, and gathered back in natural order so that both
 //                        the global loads and the global stores are coalesced; in place, scaled by
 //                        (sqrt(2 pi)/L)^3.
-// Shared memory is addressed through an XOR swizzle of the 16 float2-banks chosen (by brute force over
-// every access phase) so that all passes run at the 2-wavefront optimum of 8-byte accesses.
+// The row kernel addresses shared memory through an XOR swizzle of the 16 float2-banks chosen (by brute force
+// over every access phase) so that staging, radix passes and gather all run at the 2-wavefront optimum of
+// 8-byte accesses; the strided kernel's [position][line] tile is conflict-free as it is (lines are the fast
+// index in both global and shared memory), so it uses plain addressing.
 #include "gh_internal.cuh"
 
 namespace {
@@ -118,10 +120,11 @@ template <> struct Swz<1024, 8> { static constexpr int a = 0, b = 6, c = 31; };
 template <> struct Swz<2048, 8> { static constexpr int a = 0, b = 1, c = 7; };
 template <> struct Swz<2048, 4> { static constexpr int a = 0, b = 6, c = 31; };
 
-template <int LEN, int W> __device__ __forceinline__ int phys(int pos, int w)
+template <int LEN, int W, bool SWZ = true> __device__ __forceinline__ int phys(int pos, int w)
 {
   using S = Swz<LEN, W>;
   const int a = pos * W + w;
+  if constexpr (!SWZ) return a;
   const int l = a >> 4;
   int m = l >> S::a;
   if constexpr (S::b < 31) m ^= l >> S::b;
@@ -131,7 +134,7 @@ template <int LEN, int W> __device__ __forceinline__ int phys(int pos, int w)
 
 // One in-place radix pass of a LEN-point decimation-in-frequency transform over a [LEN][W] tile.
 // NTW is the length of the twiddle table (exp(+2 pi i j/NTW)); LEN divides NTW.
-template <int LEN, int NTW, int W, int NT, int S>
+template <int LEN, int NTW, int W, int NT, int S, bool SWZ>
 __device__ __forceinline__ void dif_pass_smem(float2 *sm, const float2 *__restrict__ tw)
 {
   constexpr int R = rad_at(LEN, S);
@@ -146,7 +149,7 @@ __device__ __forceinline__ void dif_pass_smem(float2 *sm, const float2 *__restri
     float2 u[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      addr[r] = phys<LEN, W>(p0 + r * SUB, w);
+      addr[r] = phys<LEN, W, SWZ>(p0 + r * SUB, w);
       u[r] = sm[addr[r]];
     }
     dft<R>(u);
@@ -171,7 +174,7 @@ template <int N, int W, int NT, int S>
 __device__ __forceinline__ void strided_middle(float2 *sm, const float2 *__restrict__ tw)
 {
   if constexpr (S < n_steps(N) - 1) {
-    dif_pass_smem<N, N, W, NT, S>(sm, tw);
+    dif_pass_smem<N, N, W, NT, S, false>(sm, tw);
     __syncthreads();
     strided_middle<N, W, NT, S + 1>(sm, tw);
   }
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(NT) fft_strided_kernel(const float2 *__restric
       dft<R>(u);
       twiddle_powers<R>(u, __ldg(tw + i));
 #pragma unroll
-      for (int q = 0; q < R; ++q) sm[phys<N, W>(i + q * SUB, w)] = u[q];
+      for (int q = 0; q < R; ++q) sm[phys<N, W, false>(i + q * SUB, w)] = u[q];
     }
   }
   __syncthreads();
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(NT) fft_strided_kernel(const float2 *__restric
       const int w = item % W, b = item / W;
       float2 u[R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) u[r] = sm[phys<N, W>(b * R + r, w)];
+      for (int r = 0; r < R; ++r) u[r] = sm[phys<N, W, false>(b * R + r, w)];
       dft<R>(u);
       if (w < nvalid) {
         const int f0 = dif_pos_to_freq<N>(b * R);
@@ -238,7 +241,7 @@ template <int H, int NTW, int W, int NT, int S>
 __device__ __forceinline__ void rows_passes(float2 *sm, const float2 *__restrict__ tw)
 {
   if constexpr (S < n_steps(H)) {
-    dif_pass_smem<H, NTW, W, NT, S>(sm, tw);
+    dif_pass_smem<H, NTW, W, NT, S, true>(sm, tw);
     __syncthreads();
     rows_passes<H, NTW, W, NT, S + 1>(sm, tw);
   }
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(NT) fft_c2r_rows_kernel(float2 *__restrict__ d
   const long long row0 = (long long)blockIdx.x * W;
   const int tid = threadIdx.x;
   // stage (coalesced along the row): Z[k] = (X[k] + conj X[H-k]) + i w^k (X[k] - conj X[H-k])
-#pragma unroll 2
+#pragma unroll 4
   for (int idx = tid; idx < W * H; idx += NT) {
     const int row = idx / H, k = idx % H;
     float2 z = make_float2(0.f, 0.f);
@@ -282,17 +285,18 @@ __global__ void __launch_bounds__(NT) fft_c2r_rows_kernel(float2 *__restrict__ d
   }
 }
 
-template <int N, int WSEL = 0> struct FftCfg {
+template <int N, int WSEL = 0, int NTSEL = 0> struct FftCfg {
   static constexpr int W = WSEL ? WSEL : ((N <= 512) ? 16 : (N <= 2048 ? 8 : 4));  // strided tile width (lines)
-  static constexpr int NT_S = (W * N / 16) < 64 ? 64 : ((W * N / 16) > 512 ? 512 : (W * N / 16));
+  static constexpr int NT_S0 = (W * N / 16) < 64 ? 64 : ((W * N / 16) > 512 ? 512 : (W * N / 16));
+  static constexpr int NT_S = NTSEL ? NTSEL : ((N <= 1024 && NT_S0 > 256) ? 256 : NT_S0);  // 3 CTAs/SM beat 2 fatter ones (profiles/)
   static constexpr int WR = (N <= 1024) ? 16 : (N <= 2048 ? 8 : 4);     // rows per tile of the x pass
   static constexpr int NT_R = (WR * (N / 2) / 16) < 64 ? 64 : ((WR * (N / 2) / 16) > 512 ? 512 : (WR * (N / 2) / 16));
 };
 
-template <int N, int WSEL>
+template <int N, int WSEL, int NTSEL>
 int launch_strided(gh_cuda_ctx *c, const float2 *src, float2 *dst, const StridedGeom &g, int ngroups)
 {
-  using Cfg = FftCfg<N, WSEL>;
+  using Cfg = FftCfg<N, WSEL, NTSEL>;
   auto kern = fft_strided_kernel<N, Cfg::W, Cfg::NT_S>;
   const size_t smem = (size_t)N * Cfg::W * sizeof(float2);
   GH_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -315,11 +319,11 @@ int launch_rows(gh_cuda_ctx *c, float2 *data, long long nrows, float norm)
   return 0;
 }
 
-template <int N, int WSEL = 0>
+template <int N, int WSEL = 0, int NTSEL = 0>
 int fft_field(gh_cuda_ctx *c, float2 *field)
 {
   const GhDev &d = c->d;
-  using Cfg = FftCfg<N, WSEL>;
+  using Cfg = FftCfg<N, WSEL, NTSEL>;
   const int nh = d.nh;
   const double normd = pow(sqrt(2.0 * 3.14159265358979323846) / d.l_box, 3.0);  // src/fourier.c:403
   // (1) z axis, local because k-space is ky-distributed: all nky_here*nh columns as one flat group
@@ -332,7 +336,7 @@ int fft_field(gh_cuda_ctx *c, float2 *field)
     g.grp0 = 0;
     g.blk_shift = 30;
     g.src_chunk = 0;
-    if (launch_strided<N, WSEL>(c, field, field, g, 1)) return 1;
+    if (launch_strided<N, WSEL, NTSEL>(c, field, field, g, 1)) return 1;
   }
   const float2 *ysrc = field;
   StridedGeom g;
@@ -370,7 +374,7 @@ int fft_field(gh_cuda_ctx *c, float2 *field)
   for (int z0 = 0; z0 < d.nz_here; z0 += nb) {
     const int nz = (d.nz_here - z0 < nb) ? d.nz_here - z0 : nb;
     g.grp0 = z0;
-    if (launch_strided<N, WSEL>(c, ysrc, field, g, nz)) return 1;
+    if (launch_strided<N, WSEL, NTSEL>(c, ysrc, field, g, nz)) return 1;
     if (launch_rows<N>(c, field + (size_t)z0 * d.n * nh, (long long)nz * d.n, (float)normd)) return 1;
   }
   return 0;
@@ -390,8 +394,8 @@ int gh_launch_fft_field(gh_cuda_ctx *c, float2 *field)
     case 64: return fft_field<64>(c, field);
     case 128: return fft_field<128>(c, field);
     case 256: return fft_field<256>(c, field);
-    case 512: return fft_field<512>(c, field);
-    case 1024: return (c->fft_w_override == 16) ? fft_field<1024, 16>(c, field) : fft_field<1024>(c, field);
+    case 512: return (c->fft_w_override == 256) ? fft_field<512, 0, 256>(c, field) : fft_field<512>(c, field);
+    case 1024: return (c->fft_w_override == 16) ? fft_field<1024, 16>(c, field) : (c->fft_w_override == 256) ? fft_field<1024, 0, 256>(c, field) : fft_field<1024>(c, field);
     case 2048: return fft_field<2048>(c, field);
     case 4096: return fft_field<4096>(c, field);
     default:

@@ -136,6 +136,14 @@ __global__ void __launch_bounds__(256) sigma_final_kernel(double *__restrict__ p
   }
 }
 
+// mean and variance from the (all-reduced) sums: partials[4] = <d>, partials[5] = <d^2> - <d>^2 (src/fourier.c:59-74)
+__global__ void sigma_finish_kernel(double *__restrict__ partials, double inv_ng_tot)
+{
+  const double mean = partials[0] * inv_ng_tot;
+  partials[4] = mean;
+  partials[5] = partials[1] * inv_ng_tot - mean * mean;
+}
+
 // ------------------------------------------------------------------------------------------------
 // get_HI (src/grid_tools.c:103-153) with z_of_r / dgrowth_of_r / vgrowth_of_r (src/cosmo.c:52-86) and
 // bias_HI / fraction_HI (src/user_defined.c:27-35), in place: dens <- HI mass, rvel <- Delta z_RSD.
@@ -147,8 +155,9 @@ __device__ __forceinline__ float lerp_tab(const float *__restrict__ tab, int ir,
 }
 
 __global__ void __launch_bounds__(256) get_HI_kernel(GhDev d, float *__restrict__ dens, float *__restrict__ rvel,
-                                                     float sigma2_gauss)
+                                                     const double *__restrict__ sigma_stats)
 {
+  const float sigma2_gauss = (float)sigma_stats[5];  // stays on the device: no host round trip between the stages
   const int ngx = 2 * d.nh;
   const int iy = blockIdx.y, iz = blockIdx.z;
   const AxisF ax = make_axis(d.dx, d.pos_obs[0], 0), ay = make_axis(d.dx, d.pos_obs[1], 0), az = make_axis(d.dx, d.pos_obs[2], d.iz0);
@@ -230,12 +239,20 @@ int gh_launch_sigma(gh_cuda_ctx *c)
   return 0;
 }
 
+int gh_launch_sigma_finish(gh_cuda_ctx *c)
+{
+  const double ng_tot = (double)c->d.n * ((double)c->d.n * (double)c->d.n);
+  sigma_finish_kernel<<<1, 1, 0, c->stream>>>(c->d_partials, 1.0 / ng_tot);
+  GH_LAUNCH_CHECK(c);
+  return 0;
+}
+
 int gh_launch_get_HI(gh_cuda_ctx *c)
 {
   const GhDev &d = c->d;
   dim3 grid((d.n / 2 + 255) / 256, d.n, d.nz_here);
   get_HI_kernel<<<grid, 256, 0, c->stream>>>(d, reinterpret_cast<float *>(c->gridA), reinterpret_cast<float *>(c->gridC),
-                                             (float)c->sigma2_gauss);
+                                             c->d_partials);
   GH_LAUNCH_CHECK(c);
   return 0;
 }

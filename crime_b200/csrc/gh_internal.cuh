@@ -43,6 +43,10 @@ struct gh_cuda_ctx {
   GhDev d;
   int device;
   cudaStream_t stream;
+  cudaStream_t copy_stream;        // device->host copy of the finished maps, overlaps the next realisation
+  cudaEvent_t ev_done, ev_copied;
+  bool copy_pending, sigma_ready;
+  double *h_stats;                 // pinned: sum, sumsq, mean, sigma2 of the last realisation
   ncclComm_t comm;
   bool have_comm;
   size_t slab_complex;  // complex elements per slab = nz_here*n*nh (== n*nky_here*nh)
@@ -103,6 +107,7 @@ int gh_launch_fft_field(gh_cuda_ctx *c, float2 *field);  // full c2r of one fiel
 int gh_fft_supported(int n);
 int gh_launch_radial_velocity(gh_cuda_ctx *c);
 int gh_launch_sigma(gh_cuda_ctx *c);  // leaves (sum, sumsq) in c->d_partials[0..1]
+int gh_launch_sigma_finish(gh_cuda_ctx *c);  // d_partials[4] = mean, [5] = sigma2_gauss
 int gh_launch_get_HI(gh_cuda_ctx *c);
 int gh_launch_accumulate(gh_cuda_ctx *c);
 int gh_launch_accumulate_audit(gh_cuda_ctx *c, float eps_scale, unsigned long long *d_counts);

@@ -138,19 +138,21 @@ __device__ __forceinline__ bool fast_pixel(const FastCtx &f, float cth, float tt
 // either proves the sub-particle misses every shell, or proves (shell, pixel) with all decisions clear of
 // their error bounds and deposits at once, or marks it unsure.  The azimuth is atan2 of the cell centre
 // plus the small rotation to the sub-particle (series in the tangent of the rotation angle; cells close
-// to the polar axis use atan2f per sub-particle).  Pass 2 compacts the unsure sub-particles of the warp
-// into a shared-memory queue and re-does exactly those in fp64 (gh_point_to_shell_pixel), 32 at a time,
-// so the slow path runs on full warps.
+// to the polar axis use atan2f per sub-particle).  Pass 2 compacts the unsure sub-particles of the CTA
+// into a shared-memory queue and re-does exactly those in fp64 (gh_point_to_shell_pixel) on as few warps
+// as possible.
 // AUDIT: nothing is deposited; every sub-particle is evaluated by both paths and the outcomes counted.
 template <bool AUDIT>
 __global__ void __launch_bounds__(128) accumulate_kernel(GhDev d, const float *__restrict__ mass,
                                                          const float *__restrict__ dzrsd, float *__restrict__ maps,
                                                          float eps_scale, unsigned long long *__restrict__ counts)
 {
-  __shared__ unsigned short queue[4][32 * GH_CUDA_N_SUBPART];
+  __shared__ unsigned short queue[128 * GH_CUDA_N_SUBPART];
+  __shared__ float s_dz[128], s_w[128];
+  __shared__ int s_count;
   const int ngx = 2 * d.nh;
   const int tid = threadIdx.x + 8 * threadIdx.y;  // blockDim = (8, 16)
-  const int lane = tid & 31, warp = tid >> 5;
+  if (!AUDIT && tid == 0) s_count = 0;
   const int ix = blockIdx.x * 8 + threadIdx.x, iy = blockIdx.y * 16 + threadIdx.y, iz = blockIdx.z;
   const bool active = (ix < d.n) && (iy < d.n);
   const FastCtx f = fast_ctx_of(d, eps_scale);
@@ -235,40 +237,31 @@ __global__ void __launch_bounds__(128) accumulate_kernel(GhDev d, const float *_
     atomicAdd(counts + 3, c_wrong);
     return;
   }
-  // ---- pass 2: exact path for the unsure sub-particles of this warp ----
-  const unsigned full = 0xffffffffu;
-  if (__ballot_sync(full, need != 0u) == 0u) return;
-  const int cnt = __popc(need);
-  int incl = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(full, incl, o);
-    if (lane >= o) incl += v;
-  }
-  const int total = __shfl_sync(full, incl, 31);
-  {
-    int at = incl - cnt;
+  // ---- pass 2: exact path for the unsure sub-particles of this CTA ----
+  // (a few per CTA: they are compacted into one queue so that a single warp runs the expensive fp64 code)
+  s_dz[tid] = dzf;
+  s_w[tid] = w;
+  __syncthreads();  // s_count = 0 visible; also orders the s_dz / s_w writes
+  if (need) {
+    int at = atomicAdd(&s_count, __popc(need));
     unsigned m = need;
     while (m) {
       const int isub = __ffs(m) - 1;
       m &= m - 1;
-      queue[warp][at++] = (unsigned short)((lane << 4) | isub);
+      queue[at++] = (unsigned short)((tid << 4) | isub);
     }
   }
-  __syncwarp();
-  for (int base = 0; base < total; base += 32) {
-    const int j = base + lane;
-    const bool valid = j < total;
-    const unsigned e = valid ? queue[warp][j] : 0u;
+  __syncthreads();
+  const int total = s_count;
+  for (int j = tid; j < total; j += 128) {
+    const unsigned e = queue[j];
     const int src = e >> 4, isub = e & 15;
-    const double sx = __shfl_sync(full, x0, src), sy = __shfl_sync(full, y0, src);
-    const float sdz = __shfl_sync(full, dzf, src), sw = __shfl_sync(full, w, src);
-    if (valid) {
-      long long ipix;
-      const int inu = gh_point_to_shell_pixel(t, sx + d.sub_off[isub], sy + d.sub_off[GH_CUDA_N_SUBPART + isub],
-                                              z0 + d.sub_off[2 * GH_CUDA_N_SUBPART + isub], (double)sdz, &ipix);
-      if (ipix >= 0) atomicAdd(maps + (size_t)ipix + (size_t)d.npix * inu, sw);
-    }
+    const int sx = blockIdx.x * 8 + (src & 7), sy = blockIdx.y * 16 + (src >> 3);
+    const double px = d.dx * (sx + 0.5) - d.pos_obs[0] + d.sub_off[isub];
+    const double py = d.dx * (sy + 0.5) - d.pos_obs[1] + d.sub_off[GH_CUDA_N_SUBPART + isub];
+    long long ipix;
+    const int inu = gh_point_to_shell_pixel(t, px, py, z0 + d.sub_off[2 * GH_CUDA_N_SUBPART + isub], (double)s_dz[src], &ipix);
+    if (ipix >= 0) atomicAdd(maps + (size_t)ipix + (size_t)d.npix * inu, s_w[src]);
   }
 }
 

@@ -106,8 +106,10 @@ class GetHI:
     def end_fftw(self) -> None:
         """src/fourier.c:201 (+ the grid part of param_gethi_free, src/io_gh.c:298-324)."""
         if self._ctx:
-            if self._pinned is not None:
-                self.lib.gh_cuda_host_free(self._pinned[0])
+            if self._pinned:
+                self.lib.gh_cuda_wait(self._ctx, None)
+                for p, _ in self._pinned.values():
+                    self.lib.gh_cuda_host_free(p)
                 self._pinned = None
                 self.maps_HI = None
             self.lib.gh_cuda_destroy(self._ctx)
@@ -123,6 +125,19 @@ class GetHI:
         self.sigma2_gauss = s2.value
         self.maps_HI = buf
         return buf
+
+    def run_async(self, slot: int = 0) -> np.ndarray:
+        """Enqueue a whole realisation without waiting; the maps land in pinned host buffer `slot` (0 or 1).
+        Call wait() before reading them."""
+        buf = self._host_maps(slot)
+        self._check(self.lib.gh_cuda_run_async(self._ctx, _ptr(buf)))
+        return buf
+
+    def wait(self) -> float:
+        s2 = C.c_double()
+        self._check(self.lib.gh_cuda_wait(self._ctx, C.byref(s2)))
+        self.sigma2_gauss = s2.value
+        return s2.value
 
     # -- finer stages ------------------------------------------------------------------------------
     def generate_k(self):
@@ -233,14 +248,16 @@ class GetHI:
         return int(self.lib.gh_cuda_stream(self._ctx) or 0)
 
     # -- internals ---------------------------------------------------------------------------------
-    def _host_maps(self) -> np.ndarray:
+    def _host_maps(self, slot: int = 0) -> np.ndarray:
         n = max(self.n_shells_here, 1) * self.npix
         if self._pinned is None:
+            self._pinned = {}
+        if slot not in self._pinned:
             p = C.c_void_p()
             self._check(self.lib.gh_cuda_host_alloc(C.byref(p), n * 4))
             arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n,))
-            self._pinned = (p, arr)
-        return self._pinned[1][: self.n_shells_here * self.npix].reshape(self.n_shells_here, self.npix)
+            self._pinned[slot] = (p, arr)
+        return self._pinned[slot][1][: self.n_shells_here * self.npix].reshape(self.n_shells_here, self.npix)
 
     def _check(self, rc: int):
         if rc != 0:

@@ -1,3 +1,6 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-GH_FFT_BATCH_MB=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'fft_' -s 12 -c 3 -f -o gpurun_out/prof_fft1024 python bench.py --grid 1024 --nside 512 --shells 150 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench9.log
+python -c "
+import json;d=json.loads(open('gpurun_out/bench9.log').read().strip().splitlines()[-1]);print(d['value'],d['ms_per_step'],d['e2e']['value'],d['e2e']['ms_per_step']);print(d['roofline']['stage_ms_alone'])"

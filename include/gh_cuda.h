@@ -133,6 +133,15 @@ int gh_cuda_mk_T_maps(gh_cuda_ctx *ctx, float *maps_host);
 /* whole hot path, main_gh.c:52-62: the three calls above back to back */
 int gh_cuda_run(gh_cuda_ctx *ctx, double *sigma2_gauss_out, float *maps_host);
 
+/* The same without any host synchronisation: everything is enqueued (the variance stays on the device between
+ * the stages) and the device->host copy of the maps runs on a second stream, so a caller producing many
+ * realisations overlaps the copy of one with the computation of the next:
+ *     gh_cuda_run_async(ctx, bufA); gh_cuda_run_async(ctx, bufB); gh_cuda_wait(ctx, &s2); ...
+ * gh_cuda_wait returns when everything enqueued so far, copies included, has finished.  The next realisation
+ * does not touch the device map stack before the pending copy has read it.  maps_host must be page-locked. */
+int gh_cuda_run_async(gh_cuda_ctx *ctx, float *maps_host);
+int gh_cuda_wait(gh_cuda_ctx *ctx, double *sigma2_gauss_out);
+
 /* page-locked host memory for maps / injected fields */
 int gh_cuda_host_alloc(void **ptr, unsigned long long bytes);
 int gh_cuda_host_free(void *ptr);
