@@ -312,6 +312,14 @@ def main():
                             "(SURVEY 8d): also reporting sub-particles/s")
         roofline["subparticles_per_s"] = n_sub / (cand[top] * 1e-3)
 
+    per_rank = None
+    if world > 1:
+        # every rank's own stage timers of the last pipelined step: shows load imbalance between slabs
+        mine = [stage_ms.get(k, 0.0) for k in abi.STAGE_NAMES]
+        tt = torch.tensor(mine, device=dev, dtype=torch.float64)
+        allt = [torch.zeros_like(tt) for _ in range(world)]
+        dist.all_gather(allt, tt)
+        per_rank = [{k: round(float(v), 3) for k, v in zip(abi.STAGE_NAMES, a.tolist())} for a in allt]
     n_here = g.n_shells_here
     table_bytes = sum(np.asarray(v).nbytes for k, v in tables.items() if k in abi.TABLE_FIELDS)
     maps_bytes = n_here * g.npix * 4
@@ -336,6 +344,8 @@ def main():
             "roofline": roofline,
             "stage_ms_last_e2e_step": {k: round(v, 4) for k, v in stage_ms.items()},
         }
+        if per_rank is not None:
+            line["stage_ms_by_rank"] = per_rank
         if not args.no_cpu_baseline and world == 1:
             sg = args.cpu_grid or min(n_grid, 256)
             try:

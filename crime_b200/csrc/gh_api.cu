@@ -198,11 +198,83 @@ static int apply_params(gh_cuda_ctx *c, const gh_cuda_params *p, int rank, int n
   return 0;
 }
 
+// Stream-ordered barrier across ranks: a 1-int all-reduce.  When it completes on this rank's stream every rank
+// has enqueued-and-reached the same point, so memory that peers wrote or read before it is settled.
+int gh_stream_barrier(gh_cuda_ctx *c)
+{
+  if (c->d.nranks <= 1) return 0;
+  GH_NCCL_OK(ncclAllReduce(c->d_barrier, c->d_barrier, 1, ncclInt, ncclSum, c->comm, c->stream));
+  return 0;
+}
+
+// Exchange CUDA IPC handles of the slab buffers through the communicator and map every peer's buffers, so
+// kernels can address other GPUs' slabs directly (NVLink loads / stores).  One process per GPU, one node.
+static int setup_peers(gh_cuda_ctx *c)
+{
+  const int P = c->d.nranks, me = c->d.rank;
+  GH_REQUIRE(P <= GH_MAX_RANKS, "at most %d ranks", GH_MAX_RANKS);
+  GH_CUDA_OK(cudaMalloc(&c->d_barrier, sizeof(int)));
+  GH_CUDA_OK(cudaMemsetAsync(c->d_barrier, 0, sizeof(int), c->stream));
+  const size_t hsz = sizeof(cudaIpcMemHandle_t);
+  cudaIpcMemHandle_t mine[2];
+  GH_CUDA_OK(cudaIpcGetMemHandle(&mine[0], c->gridA));
+  GH_CUDA_OK(cudaIpcGetMemHandle(&mine[1], c->gridC));
+  char *d_all = nullptr;
+  GH_CUDA_OK(cudaMalloc(&d_all, 2 * hsz * P));
+  GH_CUDA_OK(cudaMemcpyAsync(d_all + 2 * hsz * me, mine, 2 * hsz, cudaMemcpyHostToDevice, c->stream));
+  GH_NCCL_OK(ncclAllGather(d_all + 2 * hsz * me, d_all, 2 * hsz, ncclChar, c->comm, c->stream));
+  cudaIpcMemHandle_t *all = (cudaIpcMemHandle_t *)malloc(2 * hsz * P);
+  GH_REQUIRE(all, "out of host memory");
+  cudaError_t e = cudaMemcpyAsync(all, d_all, 2 * hsz * P, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d_all);
+  if (e != cudaSuccess) { free(all); gh_set_error("IPC handle exchange failed: %s", cudaGetErrorString(e)); return 1; }
+  bool ok = true;
+  for (int q = 0; q < P && ok; ++q) {
+    if (q == me) { c->peers.A[q] = c->gridA; c->peers.C[q] = c->gridC; continue; }
+    void *pa = nullptr, *pc = nullptr;
+    if (cudaIpcOpenMemHandle(&pa, all[2 * q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+        cudaIpcOpenMemHandle(&pc, all[2 * q + 1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      ok = false;
+      break;
+    }
+    c->peers.A[q] = (float2 *)pa;
+    c->peers.C[q] = (float2 *)pc;
+  }
+  free(all);
+  if (!ok) {
+    // not fatal: fall back to NCCL-only data movement (still all on the GPUs)
+    cudaGetLastError();
+    for (int q = 0; q < P; ++q) {
+      if (q != me && c->peers.A[q]) cudaIpcCloseMemHandle(c->peers.A[q]);
+      if (q != me && c->peers.C[q]) cudaIpcCloseMemHandle(c->peers.C[q]);
+      c->peers.A[q] = c->peers.C[q] = nullptr;
+    }
+    c->have_peers = false;
+    return 0;
+  }
+  c->have_peers = getenv("GH_NO_PEER") == nullptr;
+  // opt-in: see accumulate_kernel (measured: no net gain on 4 GPUs)
+  c->balance_maps = c->have_peers && P >= 4 && getenv("GH_BALANCE_MAPS") != nullptr;
+  return 0;
+}
+
 extern "C" int gh_cuda_destroy(gh_cuda_ctx *c)
 {
   if (!c) return 0;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->have_comm && c->d_barrier) {
+    // nobody may free a slab a peer could still be reading
+    ncclAllReduce(c->d_barrier, c->d_barrier, 1, ncclInt, ncclSum, c->comm, c->stream);
+    cudaStreamSynchronize(c->stream);
+  }
+  for (int q = 0; q < c->d.nranks && q < GH_MAX_RANKS; ++q) {
+    if (q == c->d.rank) continue;
+    if (c->peers.A[q]) cudaIpcCloseMemHandle(c->peers.A[q]);
+    if (c->peers.C[q]) cudaIpcCloseMemHandle(c->peers.C[q]);
+  }
+  cudaFree(c->d_barrier);
   if (c->have_comm) ncclCommDestroy(c->comm);
   cudaFree(c->gridA); cudaFree(c->gridB); cudaFree(c->gridC);
   cudaFree(c->halo_lo); cudaFree(c->halo_hi);
@@ -322,6 +394,7 @@ extern "C" int gh_cuda_create(const gh_cuda_params *p, int rank, int nranks, con
       return 1;
     }
     c->have_comm = true;
+    if (setup_peers(c)) { gh_cuda_destroy(c); return 1; }
   }
   CREATE_OK(cudaStreamSynchronize(c->stream));
 #undef CREATE_OK

@@ -168,6 +168,10 @@ struct StridedGeom {
   int grp0;                 // first group handled by this launch (plane batches)
   int blk_shift;            // source index n is split as (n >> blk_shift, n & mask): the received
   long long src_chunk;      // all-to-all blocks sit src_chunk apart (blk_shift = 30 disables the split)
+  // fused transpose (z pass, nranks > 1): output plane f belongs to rank f / nz_peer and is stored straight into
+  // that rank's receive buffer over NVLink, at block `me` of its [peer][z_local][ky_local][kx] layout
+  int peer_mode, nz_peer, me;
+  long long peer_chunk;
 };
 
 template <int N, int W, int NT, int S>
@@ -182,7 +186,7 @@ __device__ __forceinline__ void strided_middle(float2 *sm, const float2 *__restr
 
 template <int N, int W, int NT>
 __global__ void __launch_bounds__(NT) fft_strided_kernel(const float2 *__restrict__ src, float2 *__restrict__ dst,
-                                                         const float2 *__restrict__ tw, StridedGeom g)
+                                                         const float2 *__restrict__ tw, StridedGeom g, GhPeers peers)
 {
   extern __shared__ float2 sm[];
   const int tile = blockIdx.x;
@@ -228,9 +232,18 @@ __global__ void __launch_bounds__(NT) fft_strided_kernel(const float2 *__restric
       dft<R>(u);
       if (w < nvalid) {
         const int f0 = dif_pos_to_freq<N>(b * R);
-        float2 *o = dp + (long long)f0 * g.dst_stride + w;
+        if (!g.peer_mode) {
+          float2 *o = dp + (long long)f0 * g.dst_stride + w;
 #pragma unroll
-        for (int q = 0; q < R; ++q) o[(long long)(q * (N / R)) * g.dst_stride] = u[q];
+          for (int q = 0; q < R; ++q) o[(long long)(q * (N / R)) * g.dst_stride] = u[q];
+        } else {
+#pragma unroll
+          for (int q = 0; q < R; ++q) {
+            const int f = f0 + q * (N / R);
+            const int owner = f / g.nz_peer, zl = f - owner * g.nz_peer;
+            peers.C[owner][(long long)g.me * g.peer_chunk + (long long)zl * g.dst_stride + l0 + w] = u[q];
+          }
+        }
       }
     }
   }
@@ -301,7 +314,7 @@ int launch_strided(gh_cuda_ctx *c, const float2 *src, float2 *dst, const Strided
   const size_t smem = (size_t)N * Cfg::W * sizeof(float2);
   GH_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long tiles = (long long)g.tiles_per_group * ngroups;
-  kern<<<(unsigned)tiles, Cfg::NT_S, smem, c->stream>>>(src, dst, c->twiddle, g);
+  kern<<<(unsigned)tiles, Cfg::NT_S, smem, c->stream>>>(src, dst, c->twiddle, g, c->peers);
   GH_LAUNCH_CHECK(c);
   return 0;
 }
@@ -336,10 +349,17 @@ int fft_field(gh_cuda_ctx *c, float2 *field)
     g.grp0 = 0;
     g.blk_shift = 30;
     g.src_chunk = 0;
+    g.peer_mode = (d.nranks > 1 && c->have_peers) ? 1 : 0;
+    g.nz_peer = d.nz_here;
+    g.me = d.rank;
+    g.peer_chunk = (long long)d.nz_here * d.nky_here * nh;
+    // peers must be done with their receive buffers (previous field's y pass, previous realisation's maps)
+    if (g.peer_mode && gh_stream_barrier(c)) return 1;
     if (launch_strided<N, WSEL, NTSEL>(c, field, field, g, 1)) return 1;
   }
   const float2 *ysrc = field;
   StridedGeom g;
+  g.peer_mode = 0; g.nz_peer = 1; g.me = 0; g.peer_chunk = 0;
   g.lines_per_group = nh;
   g.tiles_per_group = (nh + Cfg::W - 1) / Cfg::W;
   g.dst_group_stride = (long long)d.n * nh;
@@ -347,12 +367,17 @@ int fft_field(gh_cuda_ctx *c, float2 *field)
   if (d.nranks > 1) {
     // (2) the one transpose of this field: block q (kz in q's z slab) goes to rank q
     const size_t chunk = (size_t)d.nz_here * d.nky_here * nh;
-    GH_NCCL_OK(ncclGroupStart());
-    for (int q = 0; q < d.nranks; ++q) {
-      GH_NCCL_OK(ncclSend(field + q * chunk, chunk * 2, ncclFloat, q, c->comm, c->stream));
-      GH_NCCL_OK(ncclRecv(c->gridC + q * chunk, chunk * 2, ncclFloat, q, c->comm, c->stream));
+    if (c->have_peers) {
+      // already done: the z pass stored its output into the peers' receive buffers; wait until all have
+      if (gh_stream_barrier(c)) return 1;
+    } else {
+      GH_NCCL_OK(ncclGroupStart());
+      for (int q = 0; q < d.nranks; ++q) {
+        GH_NCCL_OK(ncclSend(field + q * chunk, chunk * 2, ncclFloat, q, c->comm, c->stream));
+        GH_NCCL_OK(ncclRecv(c->gridC + q * chunk, chunk * 2, ncclFloat, q, c->comm, c->stream));
+      }
+      GH_NCCL_OK(ncclGroupEnd());
     }
-    GH_NCCL_OK(ncclGroupEnd());
     // received layout [q][z_local][ky_local][kx]; ky = q*nky_here + ky_local
     ysrc = c->gridC;
     g.src_group_stride = (long long)d.nky_here * nh;

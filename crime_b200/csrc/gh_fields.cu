@@ -2,27 +2,9 @@
 // One HBM round trip each.  Float arithmetic throughout (the reference computes in double from float
 // loads and stores floats; parity is rel <= 1e-5 on the stored floats), double only for the variance sums.
 #include "gh_internal.cuh"
+#include "gh_gethi_math.cuh"
 
 namespace {
-
-// Cell-centre coordinate along one axis, dx*(i+0.5) - pos_obs, in float without cancellation error:
-// the integer part of (0.5 - pos_obs/dx) is subtracted from the index exactly, the fraction rides on an fma.
-struct AxisF {
-  int ioff;
-  float dx, frac;
-  __device__ __forceinline__ float at(int i) const { return fmaf(dx, (float)(i - ioff), frac); }
-};
-__device__ __forceinline__ AxisF make_axis(double dx, double pos_obs, int i_origin)
-{
-  // x = dx*(i_local + i_origin + 0.5) - pos_obs = dx*((i_local - ioff) + f),  f in [0,1)
-  const double t = (double)i_origin + 0.5 - pos_obs / dx;
-  const double fl = floor(t);
-  AxisF a;
-  a.ioff = -(int)fl;
-  a.dx = (float)dx;
-  a.frac = (float)(dx * (t - fl));
-  return a;
-}
 
 // ------------------------------------------------------------------------------------------------
 // radial_velocity_from_potential (reference src/fourier.c:307-373): v = +grad(phi) by central
@@ -148,52 +130,26 @@ __global__ void sigma_finish_kernel(double *__restrict__ partials, double inv_ng
 // get_HI (src/grid_tools.c:103-153) with z_of_r / dgrowth_of_r / vgrowth_of_r (src/cosmo.c:52-86) and
 // bias_HI / fraction_HI (src/user_defined.c:27-35), in place: dens <- HI mass, rvel <- Delta z_RSD.
 // 8 B read + 8 B written per cell; the three 5001-entry float tables are read through L1.
-__device__ __forceinline__ float lerp_tab(const float *__restrict__ tab, int ir, float t)
-{
-  const float a = __ldg(tab + ir), b = __ldg(tab + ir + 1);
-  return a + (b - a) * t;
-}
-
 __global__ void __launch_bounds__(256) get_HI_kernel(GhDev d, float *__restrict__ dens, float *__restrict__ rvel,
                                                      const double *__restrict__ sigma_stats)
 {
-  const float sigma2_gauss = (float)sigma_stats[5];  // stays on the device: no host round trip between the stages
+  const GetHIConsts k = make_gethi_consts(d, (float)sigma_stats[5]);  // the variance stays on the device
   const int ngx = 2 * d.nh;
   const int iy = blockIdx.y, iz = blockIdx.z;
   const AxisF ax = make_axis(d.dx, d.pos_obs[0], 0), ay = make_axis(d.dx, d.pos_obs[1], 0), az = make_axis(d.dx, d.pos_obs[2], d.iz0);
   const float y = ay.at(iy), z = az.at(iz);
-  const float yz2 = fmaf(y, y, z * z);
-  const float mass_prefac = (float)(d.dx * d.dx * d.dx) * 0.008f;  // dx^3 * x_HI amplitude (src/user_defined.c:27-30)
-  const float idr = (float)d.glob_idr, rmax = (float)d.r_tab_max;
-  const float half_s2 = 0.5f * sigma2_gauss;
+  const float yz2 = fmaf(y, y, __fmul_rn(z, z));
   const size_t base = ((size_t)iz * d.n + iy) * ngx;
-  const int last = d.nz_tab - 1;
   // two cells per thread: rows are 8-byte aligned
   for (int ip = blockIdx.x * blockDim.x + threadIdx.x; ip < d.n / 2; ip += gridDim.x * blockDim.x) {
-    float2 dv = *reinterpret_cast<const float2 *>(dens + base + 2 * ip);
-    float2 vv = *reinterpret_cast<const float2 *>(rvel + base + 2 * ip);
-    float dd[2] = {dv.x, dv.y}, rv[2] = {vv.x, vv.y};
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const float x = ax.at(2 * ip + j);
-      const float r2 = fmaf(x, x, yz2);
-      const float r = r2 * rsqrtf(fmaxf(r2, 1e-30f));
-      // z_of_r / dgrowth_of_r / vgrowth_of_r: same bin, same weight (src/cosmo.c:52-86); r=0 and the clamp
-      // beyond the table fall out of the arithmetic (tables start at (0,1,1))
-      const float s = fminf(r, rmax) * idr;
-      const int ir = min((int)s, last - 1);
-      const float t = s - (float)ir;
-      const float redshift = lerp_tab(d.z_r2z_f, ir, t);
-      const float gd = lerp_tab(d.gd_f, ir, t);
-      const float gv = lerp_tab(d.gv_f, ir, t);
-      const float l2 = __log2f(1.f + redshift);
-      const float gfd = gd * fmaf(0.135f, exp2f(1.696f * l2), 0.904f);                        // D(r) * b_HI(z)
-      const float dens_ln = exp2f(1.4426950408889634f * (gfd * fmaf(-half_s2, gfd, dd[j])));  // exp(gfd (d - gfd s2/2))
-      dd[j] = mass_prefac * exp2f(0.6f * l2) * dens_ln;                                       // dx^3 x_HI(z) rho_LN
-      rv[j] = rv[j] * gv;                                                                     // Delta z_RSD
-    }
-    *reinterpret_cast<float2 *>(dens + base + 2 * ip) = make_float2(dd[0], dd[1]);
-    *reinterpret_cast<float2 *>(rvel + base + 2 * ip) = make_float2(rv[0], rv[1]);
+    const float2 dv = *reinterpret_cast<const float2 *>(dens + base + 2 * ip);
+    const float2 vv = *reinterpret_cast<const float2 *>(rvel + base + 2 * ip);
+    const float x0 = ax.at(2 * ip), x1 = ax.at(2 * ip + 1);
+    float2 m, dzr;
+    gh_gethi_cell(k, fmaf(x0, x0, yz2), dv.x, vv.x, m.x, dzr.x);
+    gh_gethi_cell(k, fmaf(x1, x1, yz2), dv.y, vv.y, m.y, dzr.y);
+    *reinterpret_cast<float2 *>(dens + base + 2 * ip) = m;
+    *reinterpret_cast<float2 *>(rvel + base + 2 * ip) = dzr;
   }
 }
 

@@ -39,6 +39,15 @@ struct GhDev {
   float sub_off_f[3 * GH_CUDA_N_SUBPART];
 };
 
+#define GH_MAX_RANKS 16
+
+// Peer views of the slab buffers of every rank (CUDA IPC mappings; entry [rank] is the local buffer).
+// Kernels use them to read or write other GPUs' memory over NVLink directly.
+struct GhPeers {
+  float2 *A[GH_MAX_RANKS];  // dens / HI mass
+  float2 *C[GH_MAX_RANKS];  // transpose receive buffer / radial velocity / Delta z_RSD
+};
+
 struct gh_cuda_ctx {
   GhDev d;
   int device;
@@ -49,6 +58,10 @@ struct gh_cuda_ctx {
   double *h_stats;                 // pinned: sum, sumsq, mean, sigma2 of the last realisation
   ncclComm_t comm;
   bool have_comm;
+  bool have_peers;                 // peer mappings established (nranks>1, same node)
+  bool balance_maps;               // deal map planes round-robin across ranks (peer reads)
+  GhPeers peers;
+  int *d_barrier;                  // one int, all-reduced as a stream-ordered cross-rank barrier
   size_t slab_complex;  // complex elements per slab = nz_here*n*nh (== n*nky_here*nh)
   float2 *gridA, *gridB, *gridC;  // dens, vpot, rvel/transposition scratch
   float *halo_lo, *halo_hi;       // neighbour planes of vpot (nranks>1)
@@ -110,6 +123,7 @@ int gh_launch_sigma(gh_cuda_ctx *c);  // leaves (sum, sumsq) in c->d_partials[0.
 int gh_launch_sigma_finish(gh_cuda_ctx *c);  // d_partials[4] = mean, [5] = sigma2_gauss
 int gh_launch_get_HI(gh_cuda_ctx *c);
 int gh_launch_accumulate(gh_cuda_ctx *c);
+int gh_stream_barrier(gh_cuda_ctx *c);  // every rank has reached this point of its stream
 int gh_launch_accumulate_audit(gh_cuda_ctx *c, float eps_scale, unsigned long long *d_counts);
 int gh_launch_scale_maps(gh_cuda_ctx *c, float *maps, int shell0, int nshells);
 int gh_launch_fastpath_audit(gh_cuda_ctx *c, const double *d_pos, const double *d_dz, long long n, float eps_scale,

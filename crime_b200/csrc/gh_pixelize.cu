@@ -142,10 +142,16 @@ __device__ __forceinline__ bool fast_pixel(const FastCtx &f, float cth, float tt
 // into a shared-memory queue and re-does exactly those in fp64 (gh_point_to_shell_pixel) on as few warps
 // as possible.
 // AUDIT: nothing is deposited; every sub-particle is evaluated by both paths and the outcomes counted.
-template <bool AUDIT>
+// BALANCED (opt-in, GH_BALANCE_MAPS=1, nranks >= 4): slabs near the box centre hold more in-range cells than
+// edge slabs; in this mode the planes are dealt round-robin instead: this rank takes global planes
+// z = k*P + rank and reads the HI mass and Delta z_RSD of planes it does not own straight from the owner's
+// memory over NVLink.  Measured on 4 x B200 (1024^3) it evens the ranks out at the cost of the slowest slab
+// (every rank then scatters over the whole sky instead of its own part of it), so it is off by default.
+template <bool AUDIT, bool BALANCED>
 __global__ void __launch_bounds__(128) accumulate_kernel(GhDev d, const float *__restrict__ mass,
                                                          const float *__restrict__ dzrsd, float *__restrict__ maps,
-                                                         float eps_scale, unsigned long long *__restrict__ counts)
+                                                         float eps_scale, unsigned long long *__restrict__ counts,
+                                                         GhPeers peers)
 {
   __shared__ unsigned short queue[128 * GH_CUDA_N_SUBPART];
   __shared__ float s_dz[128], s_w[128];
@@ -153,19 +159,29 @@ __global__ void __launch_bounds__(128) accumulate_kernel(GhDev d, const float *_
   const int ngx = 2 * d.nh;
   const int tid = threadIdx.x + 8 * threadIdx.y;  // blockDim = (8, 16)
   if (!AUDIT && tid == 0) s_count = 0;
-  const int ix = blockIdx.x * 8 + threadIdx.x, iy = blockIdx.y * 16 + threadIdx.y, iz = blockIdx.z;
+  const int ix = blockIdx.x * 8 + threadIdx.x, iy = blockIdx.y * 16 + threadIdx.y;
+  int iz = blockIdx.z, zg = blockIdx.z + d.iz0;  // local plane in the owner's slab, global plane
+  if (BALANCED) {
+    zg = blockIdx.z * d.nranks + d.rank;
+    const int owner = zg / d.nz_here;
+    iz = zg - owner * d.nz_here;
+    mass = reinterpret_cast<const float *>(peers.A[owner]);
+    dzrsd = reinterpret_cast<const float *>(peers.C[owner]);
+  }
   const bool active = (ix < d.n) && (iy < d.n);
   const FastCtx f = fast_ctx_of(d, eps_scale);
   const GhIndexTables t = tables_of(d);
   const double x0 = d.dx * (ix + 0.5) - d.pos_obs[0];
   const double y0 = d.dx * (iy + 0.5) - d.pos_obs[1];
-  const double z0 = d.dx * (iz + d.iz0 + 0.5) - d.pos_obs[2];
+  const double z0 = d.dx * (zg + 0.5) - d.pos_obs[2];
   float dzf = 0.f, w = 0.f;
   unsigned need = 0u;
   unsigned long long c_out = 0, c_in = 0, c_unsure = 0, c_wrong = 0;
   if (active) {
     const size_t idx = ((size_t)iz * d.n + iy) * ngx + ix;
-    dzf = dzrsd[idx];
+    // both loads up front (they may come from a peer GPU: one NVLink round trip, not two)
+    const float cell_mass = __ldcs(mass + idx);
+    dzf = __ldcs(dzrsd + idx);
     // cell centre as hi + lo floats: positions are xh + (xl + offset), one rounding of the full coordinate
     const float xh = (float)x0, yh = (float)y0, zh = (float)z0;
     const float xl = (float)(x0 - (double)xh), yl = (float)(y0 - (double)yh), zl = (float)(z0 - (double)zh);
@@ -187,7 +203,7 @@ __global__ void __launch_bounds__(128) accumulate_kernel(GhDev d, const float *_
       }
     }
     if (!culled) {
-      const double mass_sub = (double)mass[idx] / GH_CUDA_N_SUBPART;  // src/pixelize.c:203
+      const double mass_sub = (double)cell_mass / GH_CUDA_N_SUBPART;  // src/pixelize.c:203
       w = (float)mass_sub;
       // azimuth of the cell centre; sub-particles rotate it by atan(cross/dot), |cross/dot| < 0.05 when
       // the cell is further than 24 cells from the polar axis
@@ -337,8 +353,14 @@ int gh_launch_accumulate(gh_cuda_ctx *c)
 {
   const GhDev &d = c->d;
   dim3 grid((d.n + 7) / 8, (d.n + 15) / 16, d.nz_here), block(8, 16);
-  accumulate_kernel<false><<<grid, block, 0, c->stream>>>(d, reinterpret_cast<const float *>(c->gridA),
-                                                        reinterpret_cast<const float *>(c->gridC), c->maps, 1.0f, nullptr);
+  if (d.nranks > 1 && c->have_peers && c->balance_maps) {
+    // every rank's get_HI must have landed before anybody reads its slab
+    if (gh_stream_barrier(c)) return 1;
+    accumulate_kernel<false, true><<<grid, block, 0, c->stream>>>(d, nullptr, nullptr, c->maps, 1.0f, nullptr, c->peers);
+  } else {
+    accumulate_kernel<false, false><<<grid, block, 0, c->stream>>>(d, reinterpret_cast<const float *>(c->gridA),
+                                                                 reinterpret_cast<const float *>(c->gridC), c->maps, 1.0f, nullptr, c->peers);
+  }
   GH_LAUNCH_CHECK(c);
   return 0;
 }
@@ -347,8 +369,8 @@ int gh_launch_accumulate_audit(gh_cuda_ctx *c, float eps_scale, unsigned long lo
 {
   const GhDev &d = c->d;
   dim3 grid((d.n + 7) / 8, (d.n + 15) / 16, d.nz_here), block(8, 16);
-  accumulate_kernel<true><<<grid, block, 0, c->stream>>>(d, reinterpret_cast<const float *>(c->gridA),
-                                                       reinterpret_cast<const float *>(c->gridC), c->maps, eps_scale, d_counts);
+  accumulate_kernel<true, false><<<grid, block, 0, c->stream>>>(d, reinterpret_cast<const float *>(c->gridA),
+                                                              reinterpret_cast<const float *>(c->gridC), c->maps, eps_scale, d_counts, c->peers);
   GH_LAUNCH_CHECK(c);
   return 0;
 }
