@@ -152,6 +152,7 @@ static int apply_params(gh_cuda_ctx *c, const gh_cuda_params *p, int rank, int n
   d.nz_here = d.n / nranks; d.iz0 = rank * d.nz_here;
   d.nky_here = d.nz_here; d.ky0 = d.iz0;
   d.l_box = p->l_box; d.dx = p->l_box / p->n_grid;
+  d.half_inv_dx = (float)(0.5 / d.dx);
   for (int i = 0; i < 3; ++i) d.pos_obs[i] = p->pos_obs[i];
   d.seed = p->seed_rng; d.do_smoothing = p->do_smoothing; d.r2_smooth = p->r2_smooth;
   d.vfactor = p->fgrowth_0 * p->hubble_0;

@@ -13,16 +13,16 @@ namespace {
 // Two cells per thread (rows are 8-byte aligned), x neighbours through warp shuffles, y/z neighbours as
 // float2 loads that hit L1/L2 (three planes of phi stay in the 126 MB L2 while a plane is swept), so
 // DRAM sees ~4 B read + 4 B written per cell.  One CTA = one row segment of 2*blockDim cells.
-__global__ void __launch_bounds__(256) radial_velocity_kernel(GhDev d, const float *__restrict__ vpot,
+__global__ void __launch_bounds__(256) radial_velocity_kernel(GhDev d, Axes3 axes, const float *__restrict__ vpot,
                                                               const float *__restrict__ plane_lo,
                                                               const float *__restrict__ plane_hi,
                                                               float *__restrict__ rvel)
 {
   const int ngx = 2 * d.nh;
   const int iy = blockIdx.y, iz = blockIdx.z;
-  const float hidx = (float)(0.5 / d.dx);
-  const AxisF ax = make_axis(d.dx, d.pos_obs[0], 0), ay = make_axis(d.dx, d.pos_obs[1], 0), az = make_axis(d.dx, d.pos_obs[2], d.iz0);
-  const float y = ay.at(iy), z = az.at(iz);
+  const float hidx = d.half_inv_dx;
+  const AxisF ax = axes.x;
+  const float y = axes.y.at(iy), z = axes.z.at(iz);
   const int iy_hi = (iy == d.n - 1) ? 0 : iy + 1, iy_lo = (iy == 0) ? d.n - 1 : iy - 1;
   const size_t plane = (size_t)ngx * d.n;
   const float *p0 = vpot + (size_t)iz * plane;
@@ -130,14 +130,14 @@ __global__ void sigma_finish_kernel(double *__restrict__ partials, double inv_ng
 // get_HI (src/grid_tools.c:103-153) with z_of_r / dgrowth_of_r / vgrowth_of_r (src/cosmo.c:52-86) and
 // bias_HI / fraction_HI (src/user_defined.c:27-35), in place: dens <- HI mass, rvel <- Delta z_RSD.
 // 8 B read + 8 B written per cell; the three 5001-entry float tables are read through L1.
-__global__ void __launch_bounds__(256) get_HI_kernel(GhDev d, float *__restrict__ dens, float *__restrict__ rvel,
+__global__ void __launch_bounds__(256) get_HI_kernel(GhDev d, Axes3 axes, float *__restrict__ dens, float *__restrict__ rvel,
                                                      const double *__restrict__ sigma_stats)
 {
   const GetHIConsts k = make_gethi_consts(d, (float)sigma_stats[5]);  // the variance stays on the device
   const int ngx = 2 * d.nh;
   const int iy = blockIdx.y, iz = blockIdx.z;
-  const AxisF ax = make_axis(d.dx, d.pos_obs[0], 0), ay = make_axis(d.dx, d.pos_obs[1], 0), az = make_axis(d.dx, d.pos_obs[2], d.iz0);
-  const float y = ay.at(iy), z = az.at(iz);
+  const AxisF ax = axes.x;
+  const float y = axes.y.at(iy), z = axes.z.at(iz);
   const float yz2 = fmaf(y, y, __fmul_rn(z, z));
   const size_t base = ((size_t)iz * d.n + iy) * ngx;
   // two cells per thread: rows are 8-byte aligned
@@ -177,7 +177,8 @@ int gh_launch_radial_velocity(gh_cuda_ctx *c)
     hi = vpot;
   }
   dim3 grid((d.n / 2 + 255) / 256, d.n, d.nz_here);
-  radial_velocity_kernel<<<grid, 256, 0, c->stream>>>(d, vpot, lo, hi, reinterpret_cast<float *>(c->gridC));
+  const Axes3 axes = {make_axis(d.dx, d.pos_obs[0], 0), make_axis(d.dx, d.pos_obs[1], 0), make_axis(d.dx, d.pos_obs[2], d.iz0)};
+  radial_velocity_kernel<<<grid, 256, 0, c->stream>>>(d, axes, vpot, lo, hi, reinterpret_cast<float *>(c->gridC));
   GH_LAUNCH_CHECK(c);
   return 0;
 }
@@ -207,7 +208,8 @@ int gh_launch_get_HI(gh_cuda_ctx *c)
 {
   const GhDev &d = c->d;
   dim3 grid((d.n / 2 + 255) / 256, d.n, d.nz_here);
-  get_HI_kernel<<<grid, 256, 0, c->stream>>>(d, reinterpret_cast<float *>(c->gridA), reinterpret_cast<float *>(c->gridC),
+  const Axes3 axes = {make_axis(d.dx, d.pos_obs[0], 0), make_axis(d.dx, d.pos_obs[1], 0), make_axis(d.dx, d.pos_obs[2], d.iz0)};
+  get_HI_kernel<<<grid, 256, 0, c->stream>>>(d, axes, reinterpret_cast<float *>(c->gridA), reinterpret_cast<float *>(c->gridC),
                                              c->d_partials);
   GH_LAUNCH_CHECK(c);
   return 0;

@@ -11,7 +11,7 @@ struct AxisF {
   float dx, frac;
   __device__ __forceinline__ float at(int i) const { return fmaf(dx, (float)(i - ioff), frac); }
 };
-__device__ __forceinline__ AxisF make_axis(double dx, double pos_obs, int i_origin)
+__host__ __device__ __forceinline__ AxisF make_axis(double dx, double pos_obs, int i_origin)
 {
   // x = dx*(i_local + i_origin + 0.5) - pos_obs = dx*((i_local - ioff) + f),  f in [0,1)
   const double t = (double)i_origin + 0.5 - pos_obs / dx;
@@ -22,6 +22,8 @@ __device__ __forceinline__ AxisF make_axis(double dx, double pos_obs, int i_orig
   a.frac = (float)(dx * (t - fl));
   return a;
 }
+
+struct Axes3 { AxisF x, y, z; };  // built once on the host, passed to the kernels by value
 
 struct GetHIConsts {
   const float *ztab, *gdtab, *gvtab;

@@ -16,6 +16,7 @@ struct GhDev {
   int nky_here, ky0;   // k-space slab (ky rows) of this rank, before the transpose
   int nranks, rank;
   double l_box, dx, pos_obs[3];
+  float half_inv_dx;   // 0.5/dx
   // k-space realisation
   unsigned int seed;
   int do_smoothing;
