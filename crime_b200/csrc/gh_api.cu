@@ -256,7 +256,7 @@ static int setup_peers(gh_cuda_ctx *c)
   }
   c->have_peers = getenv("GH_NO_PEER") == nullptr;
   // opt-in: see accumulate_kernel (measured: no net gain on 4 GPUs)
-  c->balance_maps = c->have_peers && P >= 4 && getenv("GH_BALANCE_MAPS") != nullptr;
+  c->balance_maps = c->have_peers && P >= 4 && c->d.nz_here % (16 * P) == 0 && getenv("GH_BALANCE_MAPS") != nullptr;
   return 0;
 }
 

@@ -147,6 +147,7 @@ __device__ __forceinline__ bool fast_pixel(const FastCtx &f, float cth, float tt
 // z = k*P + rank and reads the HI mass and Delta z_RSD of planes it does not own straight from the owner's
 // memory over NVLink.  Measured on 4 x B200 (1024^3) it evens the ranks out at the cost of the slowest slab
 // (every rank then scatters over the whole sky instead of its own part of it), so it is off by default.
+#define GH_BAL_BLOCK 16
 template <bool AUDIT, bool BALANCED>
 __global__ void __launch_bounds__(128) accumulate_kernel(GhDev d, const float *__restrict__ mass,
                                                          const float *__restrict__ dzrsd, float *__restrict__ maps,
@@ -162,7 +163,13 @@ __global__ void __launch_bounds__(128) accumulate_kernel(GhDev d, const float *_
   const int ix = blockIdx.x * 8 + threadIdx.x, iy = blockIdx.y * 16 + threadIdx.y;
   int iz = blockIdx.z, zg = blockIdx.z + d.iz0;  // local plane in the owner's slab, global plane
   if (BALANCED) {
-    zg = blockIdx.z * d.nranks + d.rank;
+    // planes are dealt in blocks of GH_BAL_BLOCK consecutive planes (consecutive planes deposit into nearly the
+    // same pixels, which keeps the atomics' sectors L2-resident), block-cyclically over the ranks, each rank
+    // starting its sweep at its own slab so that at any moment every rank reads from a different owner
+    const int nblk = d.nz_here / GH_BAL_BLOCK;                      // blocks per rank
+    const int jb = (int)blockIdx.z / GH_BAL_BLOCK, jo = (int)blockIdx.z % GH_BAL_BLOCK;
+    const int kb = (jb + d.rank * (nblk / d.nranks)) % nblk;        // rotated block counter
+    zg = (kb * d.nranks + d.rank) * GH_BAL_BLOCK + jo;
     const int owner = zg / d.nz_here;
     iz = zg - owner * d.nz_here;
     mass = reinterpret_cast<const float *>(peers.A[owner]);
