@@ -103,7 +103,7 @@ static int upload_tables(gh_cuda_ctx *c, const gh_cuda_params *p)
   const int nz = p->nz_tab, nk = p->numk, nn = p->n_nu;
   // layout: doubles first, then floats
   const size_t n_dbl = (size_t)2 * nk + 4 * nz + 2 * nn;
-  const size_t n_flt = (size_t)3 * nz + nn + 1;
+  const size_t n_flt = (size_t)4 * nz + nn + 1;
   const size_t bytes = n_dbl * sizeof(double) + n_flt * sizeof(float);
   char *h = (char *)malloc(bytes);
   GH_REQUIRE(h, "out of host memory");
@@ -120,6 +120,7 @@ static int upload_tables(gh_cuda_ctx *c, const gh_cuda_params *p)
     hf[i] = (float)p->z_arr_r2z[i];
     hf[nz + i] = (float)p->growth_d_arr[i];
     hf[2 * nz + i] = (float)p->growth_v_arr[i];
+    hf[3 * nz + nn + 1 + i] = (float)p->r_arr_z2r[i];
   }
   for (int i = 0; i <= nn; ++i) {  // shell edges for the fp32 fast path
     double e;
@@ -139,7 +140,8 @@ static int upload_tables(gh_cuda_ctx *c, const gh_cuda_params *p)
   d.logkarr = dd + o_logk; d.pkarr = dd + o_pk;
   d.z_r2z = dd + o_z; d.r_r2z = dd + o_r; d.gd = dd + o_gd; d.gv = dd + o_gv;
   d.nu0 = dd + o_nu0; d.nuf = dd + o_nuf;
-  d.z_r2z_f = df; d.gd_f = df + nz; d.gv_f = df + 2 * nz; d.nu_edges_f = df + 3 * nz;
+  d.z_r2z_f = df; d.gd_f = df + nz; d.gv_f = df + 2 * nz; d.nu_edges_f = df + 3 * nz; d.r_z2r_f = df + 3 * nz + nn + 1;
+  d.inv_dz_tab = (float)(1.0 / p->dz_tab); d.z_tab_max = (float)p->z_arr_z2r[nz - 1];
   return 0;
 }
 

@@ -120,9 +120,11 @@ GH_HD int gh_point_to_shell_pixel(const GhIndexTables &t, double x, double y, do
 //   pixel-index coordinates : GH_FAST_EPS_IDX * nside                (est. <= 1.2e-6 * nside)
 //   |cos(theta)| vs 2/3     : GH_FAST_EPS_CTH                        (est. <= 4e-7)
 //   phi * 2/pi vs integers  : GH_FAST_EPS_TT                         (est. <= 1e-6)
+//   radius vs a shell edge  : GH_FAST_EPS_R  Mpc/h                   (est. <= 3e-3)
 #define GH_FAST_EPS_NU 4e-3f
 #define GH_FAST_EPS_IDX 6e-6f
 #define GH_FAST_EPS_CTH 3e-6f
 #define GH_FAST_EPS_TT 6e-6f
+#define GH_FAST_EPS_R 2e-2f   /* Mpc/h: shell-edge radii of a cell (est. discrepancy <= 3e-3) */
 
 enum { GH_FAST_OUT = 0, GH_FAST_IN = 1, GH_FAST_UNSURE = 2 };

@@ -34,6 +34,8 @@ struct GhDev {
   int n_nu, n_nu_pad, irregular;
   const double *nu0, *nuf;
   const float *nu_edges_f;  // n_nu+1 float shell edges for the fp32 fast path
+  const float *r_z2r_f;     // float copy of r_arr_z2r (uniform in z, step dz_tab)
+  float inv_dz_tab, z_tab_max;
   double nu_min, nu_max, inv_dnu;
   double z_lo_cull, z_hi_cull; // redshift window outside of which no sub-particle can land in a shell
   double sub_off[3 * GH_CUDA_N_SUBPART];

@@ -47,6 +47,9 @@ struct FastCtx {
   float eps_nu, cth_lo, cth_hi, eps_tt, fns, eidx;
   float nu_out_lo, nu_out_hi;  // certainly outside every shell below / above these
   int ns, n_nu, ir_max;
+  const float *rtab;           // r(z), uniform in z
+  float inv_dz, z_tab_max, r_last, eps_r;
+  int iz_max;
 };
 
 __device__ __forceinline__ FastCtx fast_ctx_of(const GhDev &d, float eps_scale)
@@ -61,6 +64,8 @@ __device__ __forceinline__ FastCtx fast_ctx_of(const GhDev &d, float eps_scale)
   f.ns = (int)d.nside; f.fns = (float)f.ns; f.eidx = GH_FAST_EPS_IDX * eps_scale * f.fns;
   f.n_nu = d.n_nu; f.ir_max = d.nz_tab - 2;
   f.nu_out_lo = __ldg(d.nu_edges_f) - f.eps_nu; f.nu_out_hi = __ldg(d.nu_edges_f + d.n_nu) + f.eps_nu;
+  f.rtab = d.r_z2r_f; f.inv_dz = d.inv_dz_tab; f.z_tab_max = d.z_tab_max; f.r_last = __ldg(d.r_z2r_f + d.nz_tab - 1);
+  f.eps_r = GH_FAST_EPS_R * eps_scale; f.iz_max = d.nz_tab - 2;
   return f;
 }
 
@@ -72,6 +77,73 @@ __device__ __forceinline__ float z_of_r_f(const FastCtx &f, float r)
   const float a = __ldg(f.ztab + ir), b = __ldg(f.ztab + ir + 1);
   const float zr = fmaf(b - a, s - (float)ir, a);
   return (r >= f.r_tab_max) ? f.z_last : zr;
+}
+
+// float r_of_z (src/cosmo.c:40-50)
+__device__ __forceinline__ float r_of_z_f(const FastCtx &f, float z)
+{
+  const float s = fmaxf(z, 0.f) * f.inv_dz;
+  const int iz = min((int)s, f.iz_max);
+  const float a = __ldg(f.rtab + iz), b = __ldg(f.rtab + iz + 1);
+  const float r = fmaf(b - a, s - (float)iz, a);
+  return (z >= f.z_tab_max) ? f.r_last : r;
+}
+
+// Shell boundaries of one cell, as squared radii.  Every sub-particle of the cell has the same Delta z_RSD, so
+// a shell edge nu_j is crossed at one radius r_j(dz) for the whole cell: r < r_j <=> nu > nu_j (z_of_r is
+// monotone).  The cull's redshift bracket bounds which edges any of the cell's sub-particles can reach; with at
+// most two of them the per-sub-particle shell is two comparisons of r^2 instead of a table look-up, a division
+// and an edge search.  shell[] = shell below the inner edge, between the two, beyond the outer one (-1 = outside
+// every shell); within eps_r of an edge the sub-particle is unsure.  ok = false: more than two edges in reach
+// (shells thinner than cells) -> the caller uses the per-sub-particle frequency path.
+struct CellShells {
+  float lo_a, hi_a, lo_b, hi_b;
+  int shell[3];
+  bool ok;
+};
+
+__device__ __forceinline__ CellShells cell_shells(const FastCtx &f, float zs_lo, float zs_hi, float dz)
+{
+  CellShells c;
+  c.ok = false;
+  c.lo_a = c.hi_a = c.lo_b = c.hi_b = 3.0e38f;
+  c.shell[0] = c.shell[1] = c.shell[2] = -1;
+  const float nu_hi = 1420.40575177f * rcp_ftz(1.0f + zs_lo), nu_lo = 1420.40575177f * rcp_ftz(1.0f + zs_hi);
+  // j_min = first edge >= nu_lo
+  int j = (int)ceilf((nu_lo - f.nu_min) * f.inv_dnu);
+  j = max(0, min(j, f.n_nu));
+  for (int it = 0; it < 4 && j > 0 && __ldg(f.edges + j - 1) >= nu_lo; ++it) --j;
+  for (int it = 0; it < 4 && j <= f.n_nu && __ldg(f.edges + j) < nu_lo; ++it) ++j;
+  if (j > 0 && __ldg(f.edges + j - 1) >= nu_lo) return c;        // search did not converge (very uneven table)
+  if (j <= f.n_nu && __ldg(f.edges + j) < nu_lo) return c;
+  // edges in reach: j, j+1, ... while <= nu_hi
+  int ne = 0;
+  while (j + ne <= f.n_nu && __ldg(f.edges + j + ne) <= nu_hi) {
+    if (++ne > 2) return c;
+  }
+  // shell just below edge j is j-1 (or outside when j == 0); nu decreases with r, so the innermost radii see
+  // the highest shell
+  auto shell_or_out = [&](int g) { return (g >= 0 && g < f.n_nu) ? g : -1; };
+  if (ne == 0) {
+    c.shell[0] = shell_or_out(j - 1);
+  } else {
+    const int j_in = j + ne - 1;  // highest-frequency edge in reach = smallest radius
+    {
+      const float r = r_of_z_f(f, 1420.40575177f * rcp_ftz(__ldg(f.edges + j_in)) - 1.0f - dz);
+      const float a = fmaxf(r - f.eps_r, 0.f), b = r + f.eps_r;
+      c.lo_a = a * a; c.hi_a = b * b;
+    }
+    c.shell[0] = shell_or_out(j_in);       // r < r_edge: nu >= edge j_in
+    c.shell[1] = shell_or_out(j_in - 1);
+    if (ne == 2) {
+      const float r = r_of_z_f(f, 1420.40575177f * rcp_ftz(__ldg(f.edges + j)) - 1.0f - dz);
+      const float a = fmaxf(r - f.eps_r, 0.f), b = r + f.eps_r;
+      c.lo_b = a * a; c.hi_b = b * b;
+      c.shell[2] = shell_or_out(j - 1);
+    }
+  }
+  c.ok = true;
+  return c;
 }
 
 // shell of a frequency: GH_FAST_IN (sure, shell in inu), GH_FAST_OUT (surely outside), GH_FAST_UNSURE
@@ -216,6 +288,7 @@ __global__ void __launch_bounds__(128) accumulate_kernel(GhDev d, const float *_
       // the cell is further than 24 cells from the polar axis
       const bool series = rp2 > 576.0f * (float)(d.dx * d.dx);
       const float phi_c = atan2f(yh, xh);
+      const CellShells cs = cell_shells(f, zs_lo, zs_hi, dzf);
 #pragma unroll 2
       for (int isub = 0; isub < GH_CUDA_N_SUBPART; ++isub) {
         const float ox = xl + d.sub_off_f[isub], oy = yl + d.sub_off_f[GH_CUDA_N_SUBPART + isub];
@@ -223,9 +296,16 @@ __global__ void __launch_bounds__(128) accumulate_kernel(GhDev d, const float *_
         const float q = fmaf(x, x, y * y);
         const float r2 = fmaf(z, z, q);
         const float inv_r = rsqrt_ftz(r2);
-        const float nu = 1420.40575177f * rcp_ftz(1.0f + (z_of_r_f(f, r2 * inv_r) + dzf));
-        int inu, pix = -1;
-        int st = fast_shell(f, nu, inu);
+        int inu, pix = -1, st;
+        if (cs.ok) {
+          // two comparisons of r^2 against the cell's shell-edge radii
+          const bool in0 = r2 < cs.lo_a, in1 = (r2 > cs.hi_a) & (r2 < cs.lo_b), in2 = r2 > cs.hi_b;
+          inu = in0 ? cs.shell[0] : (in1 ? cs.shell[1] : cs.shell[2]);
+          st = (in0 | in1 | in2) ? (inu >= 0 ? GH_FAST_IN : GH_FAST_OUT) : GH_FAST_UNSURE;
+        } else {
+          const float nu = 1420.40575177f * rcp_ftz(1.0f + (z_of_r_f(f, r2 * inv_r) + dzf));
+          st = fast_shell(f, nu, inu);
+        }
         if (st == GH_FAST_IN) {
           float phi;
           if (series) {
