@@ -245,14 +245,25 @@ static int setup_peers(gh_cuda_ctx *c)
     c->peers.C[q] = (float2 *)pc;
   }
   free(all);
+  // every rank must take the same route: agree on min(ok) over the ranks
+  {
+    cudaGetLastError();
+    int flag = ok ? 1 : 0;
+    GH_CUDA_OK(cudaMemcpyAsync(c->d_barrier, &flag, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    GH_NCCL_OK(ncclAllReduce(c->d_barrier, c->d_barrier, 1, ncclInt, ncclMin, c->comm, c->stream));
+    GH_CUDA_OK(cudaMemcpyAsync(&flag, c->d_barrier, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    GH_CUDA_OK(cudaStreamSynchronize(c->stream));
+    GH_CUDA_OK(cudaMemsetAsync(c->d_barrier, 0, sizeof(int), c->stream));
+    ok = flag == 1;
+  }
   if (!ok) {
     // not fatal: fall back to NCCL-only data movement (still all on the GPUs)
-    cudaGetLastError();
     for (int q = 0; q < P; ++q) {
       if (q != me && c->peers.A[q]) cudaIpcCloseMemHandle(c->peers.A[q]);
       if (q != me && c->peers.C[q]) cudaIpcCloseMemHandle(c->peers.C[q]);
       c->peers.A[q] = c->peers.C[q] = nullptr;
     }
+    cudaGetLastError();
     c->have_peers = false;
     return 0;
   }

@@ -234,19 +234,25 @@ static void write_nu_table(const ParamGetHI *par)
   fclose(f);
 }
 
-/* Every rank writes the shells it owns (the reference gathers everything on rank 0 first). */
+/* Every rank writes the shells it owns (the reference gathers everything on rank 0 first and writes the files
+ * one after the other, with a float copy per map, src/io_gh.c:69-131).  One file per shell, so the shells are
+ * written concurrently: the byte-swap runs on several cores and the file system sees several streams. */
 void write_maps(ParamGetHI *par)
 {
   if (par->rank == 0) write_nu_table(par); /* the shipped Makefile's -D_DEBUG output, src/io_gh.c:112-114 */
   print_info("*** Writing files %s_###.fits\n", par->prefixOut);
   const long npix = 12 * par->n_side * par->n_side;
+  int n_exist = 0, n_fail = 0;
+#pragma omp parallel for schedule(dynamic) reduction(+ : n_exist, n_fail)
   for (int s = 0; s < par->n_shells_here; s++) {
     char fn[300];
     snprintf(fn, sizeof(fn), "%s_%03d.fits", par->prefixOut, par->shell0_here + s + 1);
     const int rc = gh_write_healpix_map(par->maps_HI + (size_t)s * npix, par->n_side, fn);
-    if (rc == 1) report_error(0, "%s exists and was left untouched\n", fn);
-    else if (rc) report_error(1, "could not write %s\n", fn);
+    if (rc == 1) n_exist++;
+    else if (rc) n_fail++;
   }
+  if (n_exist) report_error(0, "%d of the %s_###.fits files exist and were left untouched\n", n_exist, par->prefixOut);
+  if (n_fail) report_error(1, "could not write %d of the %s_###.fits files\n", n_fail, par->prefixOut);
 }
 
 void param_gethi_free(ParamGetHI *par)

@@ -22,3 +22,29 @@ def test_slab_decomposition_matches_single_gpu(world, n_grid, n_side):
            "--master-port", str(29400 + world), str(ROOT / "tests" / "multi_gpu_worker.py"), str(n_grid), str(n_side)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert "MULTI_GPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_c_host_fork_launcher_two_gpus(tmp_path):
+    """GH_NGPUS=2 ./GetHI file: the C host forks one rank per GPU, passes the NCCL id through pipes, and every
+    rank writes the shells it owns; the files equal a single-GPU run's."""
+    import os
+    import numpy as np
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, str(ROOT))
+    from crime_b200 import host
+    from oracle.binding import write_nutable, write_param_file
+    write_nutable(tmp_path / "nu.txt", 10)
+    outs = {}
+    for tag, env in (("one", {}), ("two", {"GH_NGPUS": "2"})):
+        write_param_file(tmp_path / f"{tag}.ini", n_grid=64, n_side=16, nutable=tmp_path / "nu.txt",
+                         pk_file=ROOT / "data" / "Pk_synth.dat", prefix=tmp_path / tag, seed=12)
+        r = subprocess.run([str(host.HOST_EXE), str(tmp_path / f"{tag}.ini")], capture_output=True, text=True, timeout=300,
+                           env={**os.environ, **env})
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs[tag] = [host.read_healpix_map(tmp_path / f"{tag}_{s + 1:03d}.fits")[0] for s in range(10)]
+    for a, b in zip(outs["one"], outs["two"]):
+        assert np.array_equal(a != 0, b != 0)
+        nz = a != 0
+        if nz.any():
+            assert np.abs(b[nz] / a[nz] - 1).max() < 1e-5
