@@ -269,21 +269,30 @@ __global__ void __launch_bounds__(NT) fft_c2r_rows_kernel(float2 *__restrict__ d
   extern __shared__ float2 sm[];
   const long long row0 = (long long)blockIdx.x * W;
   const int tid = threadIdx.x;
-  // stage (coalesced along the row): Z[k] = (X[k] + conj X[H-k]) + i w^k (X[k] - conj X[H-k])
+  // stage (coalesced along the row, each input element loaded once): with A = X[k], B = conj X[H-k], E = A + B,
+  // T = w^k (A - B):  Z[k] = E + iT  and  Z[H-k] = conj(E - iT).  k = 0 pairs X[0] with X[H] (their imaginary
+  // parts are not part of a half-complex spectrum and are never read) and also owns the self-paired Z[H/2].
 #pragma unroll 4
-  for (int idx = tid; idx < W * H; idx += NT) {
-    const int row = idx / H, k = idx % H;
-    float2 z = make_float2(0.f, 0.f);
+  for (int idx = tid; idx < W * (H / 2); idx += NT) {
+    const int row = idx / (H / 2), k = idx % (H / 2);
+    float2 zk = make_float2(0.f, 0.f), zm = make_float2(0.f, 0.f);
     if (row0 + row < nrows) {
       const float2 *x = data + (row0 + row) * ROW_STRIDE;
       float2 a = x[k], bb = x[H - k];
-      bb.y = -bb.y;
-      if (k == 0) { a.y = 0.f; bb.y = 0.f; }  // Im(DC), Im(Nyquist) are not part of a half-complex spectrum
-      const float2 e = cadd(a, bb), d = csub(a, bb);
-      const float2 t = cmul(__ldg(tw + k), d);
-      z = make_float2(e.x - t.y, e.y + t.x);
+      if (k == 0) {
+        const float2 mid = x[H / 2];
+        zk = make_float2(a.x + bb.x, a.x - bb.x);
+        zm = make_float2(2.f * mid.x, -2.f * mid.y);   // Z[H/2] = 2 conj X[H/2]
+      } else {
+        bb.y = -bb.y;
+        const float2 e = cadd(a, bb), d = csub(a, bb);
+        const float2 t = cmul(__ldg(tw + k), d);
+        zk = make_float2(e.x - t.y, e.y + t.x);
+        zm = make_float2(e.x + t.y, t.x - e.y);
+      }
     }
-    sm[phys<H, W>(k, row)] = z;
+    sm[phys<H, W>(k, row)] = zk;
+    sm[phys<H, W>(k == 0 ? H / 2 : H - k, row)] = zm;
   }
   __syncthreads();
   rows_passes<H, N, W, NT, 0>(sm, tw);
