@@ -382,7 +382,7 @@ extern "C" int gh_cuda_create(const gh_cuda_params *p, int rank, int nranks, con
     CREATE_OK(cudaMalloc(&c->halo_hi, plane_bytes));
     CREATE_OK(cudaMalloc(&c->maps_recv, (size_t)shells_per_rank * d.npix * sizeof(float)));
   }
-  CREATE_OK(cudaMalloc(&c->d_partials, sizeof(double) * (8 + 2 * (size_t)c->n_sm * 8)));
+  CREATE_OK(cudaMalloc(&c->d_partials, sizeof(double) * (8 + 2 * ((size_t)c->n_sm * 8 + (size_t)d.nz_here * d.n))));
   CREATE_OK(cudaMalloc(&c->d_prefac, sizeof(double) * d.n_nu_pad));
   CREATE_OK(cudaMemcpyAsync(c->d_prefac, c->h_prefac, sizeof(double) * d.n_nu_pad, cudaMemcpyHostToDevice, c->stream));
   {
@@ -493,6 +493,7 @@ extern "C" int gh_cuda_generate_k(gh_cuda_ctx *c)
 extern "C" int gh_cuda_fft_fields(gh_cuda_ctx *c)
 {
   GH_CTX(c);
+  c->fft_stats_blocks = 0;
   StageTimer t(c, GH_T_FFT);
   if (gh_launch_fft_field(c, c->gridA)) return 1;  // src/fourier.c:391
   return gh_launch_fft_field(c, c->gridB);         // src/fourier.c:392
@@ -545,6 +546,7 @@ extern "C" int gh_cuda_create_d_and_vr_fields(gh_cuda_ctx *c, double *sigma2_out
 extern "C" int gh_cuda_get_HI(gh_cuda_ctx *c)
 {
   GH_CTX(c);
+  c->fft_stats_blocks = 0;  // the density grid turns into HI mass
   GH_REQUIRE(c->sigma_ready, "gh_cuda_get_HI: sigma2_gauss not set (run create_d_and_vr_fields or set it)");
   StageTimer t(c, GH_T_GETHI);
   return gh_launch_get_HI(c);
@@ -700,6 +702,7 @@ extern "C" int gh_cuda_upload_grid(gh_cuda_ctx *c, int which, const float *slab_
   GH_CTX(c);
   float2 *g = grid_ptr(c, which);
   GH_REQUIRE(g && slab_in, "gh_cuda_upload_grid: bad grid id %d or null input", which);
+  if (which == GH_GRID_DENS) c->fft_stats_blocks = 0;  // the FFT's partial sums no longer describe this grid
   GH_CUDA_OK(cudaMemcpyAsync(g, slab_in, c->slab_complex * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
   GH_CUDA_OK(cudaStreamSynchronize(c->stream));
   return 0;

@@ -260,9 +260,12 @@ __device__ __forceinline__ void rows_passes(float2 *sm, const float2 *__restrict
   }
 }
 
-template <int N, int W, int NT>
+// STATS: also leave this CTA's sum and sum of squares of the real cells it produced in stats[2 + 2*blockIdx.x ..]
+// (float product, double accumulation, fixed order: compute_sigma_dens, src/fourier.c:24-76, without re-reading
+// the density field).
+template <int N, int W, int NT, bool STATS>
 __global__ void __launch_bounds__(NT) fft_c2r_rows_kernel(float2 *__restrict__ data, const float2 *__restrict__ tw,
-                                                          long long nrows, float norm)
+                                                          long long nrows, float norm, double *__restrict__ stats)
 {
   constexpr int H = N / 2;
   constexpr int ROW_STRIDE = N / 2 + 1;  // complex elements per row (= 2(N/2+1) floats)
@@ -297,12 +300,35 @@ __global__ void __launch_bounds__(NT) fft_c2r_rows_kernel(float2 *__restrict__ d
   __syncthreads();
   rows_passes<H, N, W, NT, 0>(sm, tw);
   // gather in natural order (coalesced along the row): z[m] = x[2m] + i x[2m+1]
+  double s1 = 0.0, s2 = 0.0;
 #pragma unroll 2
   for (int idx = tid; idx < W * H; idx += NT) {
     const int row = idx / H, m = idx % H;
     if (row0 + row < nrows) {
       const float2 z = sm[phys<H, W>(freq_to_dif_pos<H>(m), row)];
-      data[(row0 + row) * ROW_STRIDE + m] = make_float2(z.x * norm, z.y * norm);
+      const float2 v = make_float2(z.x * norm, z.y * norm);
+      data[(row0 + row) * ROW_STRIDE + m] = v;
+      if (STATS) {
+        s1 += (double)v.x + (double)v.y;
+        s2 += (double)__fmul_rn(v.x, v.x) + (double)__fmul_rn(v.y, v.y);
+      }
+    }
+  }
+  if (STATS) {
+    __shared__ double red[2][NT / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_down_sync(0xffffffffu, s1, o);
+      s2 += __shfl_down_sync(0xffffffffu, s2, o);
+    }
+    if ((tid & 31) == 0) { red[0][tid >> 5] = s1; red[1][tid >> 5] = s2; }
+    __syncthreads();
+    if (tid == 0) {
+      double a = 0.0, b = 0.0;
+#pragma unroll
+      for (int i = 0; i < NT / 32; ++i) { a += red[0][i]; b += red[1][i]; }
+      stats[2 + 2 * (size_t)blockIdx.x] = a;
+      stats[3 + 2 * (size_t)blockIdx.x] = b;
     }
   }
 }
@@ -328,16 +354,17 @@ int launch_strided(gh_cuda_ctx *c, const float2 *src, float2 *dst, const Strided
   return 0;
 }
 
-template <int N>
-int launch_rows(gh_cuda_ctx *c, float2 *data, long long nrows, float norm)
+template <int N, bool STATS>
+int launch_rows(gh_cuda_ctx *c, float2 *data, long long nrows, float norm, long long first_block)
 {
   using Cfg = FftCfg<N>;
-  auto kern = fft_c2r_rows_kernel<N, Cfg::WR, Cfg::NT_R>;
+  auto kern = fft_c2r_rows_kernel<N, Cfg::WR, Cfg::NT_R, STATS>;
   const size_t smem = (size_t)Cfg::WR * (N / 2) * sizeof(float2);
   GH_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long blocks = (nrows + Cfg::WR - 1) / Cfg::WR;
-  kern<<<(unsigned)blocks, Cfg::NT_R, smem, c->stream>>>(data, c->twiddle, nrows, norm);
+  kern<<<(unsigned)blocks, Cfg::NT_R, smem, c->stream>>>(data, c->twiddle, nrows, norm, c->d_partials + 2 * first_block);
   GH_LAUNCH_CHECK(c);
+  if (STATS) c->fft_stats_blocks = (int)(first_block + blocks);
   return 0;
 }
 
@@ -409,7 +436,12 @@ int fft_field(gh_cuda_ctx *c, float2 *field)
     const int nz = (d.nz_here - z0 < nb) ? d.nz_here - z0 : nb;
     g.grp0 = z0;
     if (launch_strided<N, WSEL, NTSEL>(c, ysrc, field, g, nz)) return 1;
-    if (launch_rows<N>(c, field + (size_t)z0 * d.n * nh, (long long)nz * d.n, (float)normd)) return 1;
+    const long long first_block = ((long long)z0 * d.n) / Cfg::WR;
+    if (field == c->gridA) {
+      if (launch_rows<N, true>(c, field + (size_t)z0 * d.n * nh, (long long)nz * d.n, (float)normd, first_block)) return 1;
+    } else {
+      if (launch_rows<N, false>(c, field + (size_t)z0 * d.n * nh, (long long)nz * d.n, (float)normd, 0)) return 1;
+    }
   }
   return 0;
 }

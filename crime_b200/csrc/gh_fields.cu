@@ -186,6 +186,12 @@ int gh_launch_radial_velocity(gh_cuda_ctx *c)
 int gh_launch_sigma(gh_cuda_ctx *c)
 {
   const GhDev &d = c->d;
+  if (c->fft_stats_blocks > 0) {
+    // the density FFT's last pass already produced the per-CTA partial sums
+    sigma_final_kernel<<<1, 256, 0, c->stream>>>(c->d_partials, c->fft_stats_blocks);
+    GH_LAUNCH_CHECK(c);
+    return 0;
+  }
   int blocks = c->n_sm * 8;
   const long long nrows = (long long)d.nz_here * d.n;
   if (blocks > nrows) blocks = (int)nrows;
