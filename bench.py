@@ -33,7 +33,8 @@ sys.path.insert(0, str(ROOT))
 
 WORKLOADS = {1: (512, 256, 64), 2: (1024, 512, 150), 4: (1024, 512, 150), 8: (2048, 1024, 150)}
 # algorithmic HBM bytes per cell of each stage (single-GPU FFT has no transpose pass)
-STAGE_BYTES_PER_CELL = {"kgen": 8.0, "fft": 32.0, "fft_multi": 48.0, "vel": 8.0, "sigma": 4.0, "get_HI": 16.0, "maps": 8.0}
+# (the variance sums are produced inside the density FFT's last pass: no traffic of their own)
+STAGE_BYTES_PER_CELL = {"kgen": 8.0, "fft": 32.0, "fft_multi": 48.0, "vel": 8.0, "sigma": 0.0, "get_HI": 16.0, "maps": 8.0}
 
 
 def load_tables(n_nu: int) -> dict:

@@ -83,14 +83,14 @@ def full(tag, rep, n_grid):
         except Exception:
             pass
     (HERE / f"{tag}_ncu_full.md").write_text("\n".join(md) + "\n")
-    stage_of = {"kgen_kernel": "kgen", "radial_velocity_kernel": "vel", "get_HI_kernel": "get_HI", "accumulate_kernel<0>": "maps",
+    stage_of = {"kgen_kernel": "kgen", "radial_velocity_kernel": "vel", "get_HI_kernel": "get_HI", "accumulate_kernel": "maps",
                 "sigma_partial_kernel": "sigma"}
     tf = HERE / "roofline_traffic.json"
     cur = json.loads(tf.read_text()) if tf.exists() else {}
     for k, v in traffic.items():
-        base = k.split("<")[0] if k.startswith("fft") else k
-        if k in stage_of:
-            cur[f"{stage_of[k]}:{n_grid}"] = v
+        base = k.split("<")[0]
+        if base in stage_of:
+            cur[f"{stage_of[base]}:{n_grid}"] = v
         cur[f"kernel:{base}:{n_grid}"] = v
     # fft stage = 2 fields x (2 strided + 1 rows)
     fs = [v for k, v in traffic.items() if k.startswith("fft_strided")]
