@@ -342,7 +342,6 @@ extern "C" int gh_cuda_create(const gh_cuda_params *p, int rank, int nranks, con
     // y/x FFT plane batch in MB (GH_FFT_BATCH_MB; 0 / unset = whole slab per pass)
     const char *e = getenv("GH_FFT_BATCH_MB");
     const double mb = e ? atof(e) : 0.0;  // measured: batching through L2 does not pay on B200 (profiles/), off by default
-    c->fft_w_override = getenv("GH_FFT_W") ? atoi(getenv("GH_FFT_W")) : 0;
     c->fft_batch_bytes = mb > 0 ? (size_t)(mb * 1024.0 * 1024.0) : (size_t)1 << 60;
   }
 

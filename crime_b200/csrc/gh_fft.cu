@@ -460,8 +460,8 @@ int gh_launch_fft_field(gh_cuda_ctx *c, float2 *field)
     case 64: return fft_field<64>(c, field);
     case 128: return fft_field<128>(c, field);
     case 256: return fft_field<256>(c, field);
-    case 512: return (c->fft_w_override == 256) ? fft_field<512, 0, 256>(c, field) : fft_field<512>(c, field);
-    case 1024: return (c->fft_w_override == 16) ? fft_field<1024, 16>(c, field) : (c->fft_w_override == 256) ? fft_field<1024, 0, 256>(c, field) : fft_field<1024>(c, field);
+    case 512: return fft_field<512>(c, field);
+    case 1024: return fft_field<1024>(c, field);
     case 2048: return fft_field<2048>(c, field);
     case 4096: return fft_field<4096>(c, field);
     default:

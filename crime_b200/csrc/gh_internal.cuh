@@ -84,7 +84,6 @@ struct gh_cuda_ctx {
   unsigned long long launches;
   int n_sm;
   int fft_stats_blocks;    // >0: the density FFT left that many per-CTA (sum, sumsq) partials in d_partials
-  int fft_w_override;      // experiment knob: strided tile width for N=1024
   size_t fft_batch_bytes;  // plane batch of the fused y/x FFT passes (kept L2-resident)
 };
 
