@@ -104,9 +104,20 @@ static int upload_tables(gh_cuda_ctx *c, const gh_cuda_params *p)
   // layout: doubles first, then floats
   const size_t n_dbl = (size_t)2 * nk + 4 * nz + 2 * nn;
   const size_t n_flt = (size_t)4 * nz + nn + 1;
-  const size_t bytes = n_dbl * sizeof(double) + n_flt * sizeof(float);
-  char *h = (char *)malloc(bytes);
-  GH_REQUIRE(h, "out of host memory");
+  const size_t bytes = (n_dbl * sizeof(double) + n_flt * sizeof(float) + 7) & ~(size_t)7;
+  // pinned staging, two buffers used alternately: the copy is ordered on the compute stream behind the previous
+  // realisation's kernels and the host does not wait for it (a realisation can be queued while the last one runs)
+  const int k = c->stage_next;
+  c->stage_next ^= 1;
+  if (!c->h_stage[k]) {
+    GH_CUDA_OK(cudaMallocHost((void **)&c->h_stage[k], bytes + sizeof(c->h_prefac)));
+    GH_CUDA_OK(cudaEventCreateWithFlags(&c->ev_stage[k], cudaEventDisableTiming));
+  } else {
+    GH_CUDA_OK(cudaEventSynchronize(c->ev_stage[k]));
+  }
+  GH_REQUIRE(!c->d_tables || bytes == c->tables_bytes, "table sizes changed; create a new context");
+  c->stage_cur = k;
+  char *h = c->h_stage[k];
   double *hd = (double *)h;
   float *hf = (float *)(h + n_dbl * sizeof(double));
   size_t o = 0;
@@ -128,13 +139,9 @@ static int upload_tables(gh_cuda_ctx *c, const gh_cuda_params *p)
     else e = p->nu_min + (p->nu_max - p->nu_min) * (double)(i == 0 ? -1 : i) / nn;  // shell 0 also takes (nu_min-dnu, nu_min): C truncation, src/pixelize.c:216
     hf[3 * nz + i] = (float)e;
   }
-  cudaError_t e = cudaSuccess;
-  if (!c->d_tables) { e = cudaMalloc(&c->d_tables, bytes); c->tables_bytes = bytes; }
-  else if (bytes != c->tables_bytes) { free(h); gh_set_error("table sizes changed; create a new context"); return 1; }
-  if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_tables, h, bytes, cudaMemcpyHostToDevice, c->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  free(h);
-  GH_REQUIRE(e == cudaSuccess, "table upload failed: %s", cudaGetErrorString(e));
+  if (!c->d_tables) { GH_CUDA_OK(cudaMalloc(&c->d_tables, bytes)); c->tables_bytes = bytes; }
+  GH_CUDA_OK(cudaMemcpyAsync(c->d_tables, h, bytes, cudaMemcpyHostToDevice, c->stream));
+  GH_CUDA_OK(cudaEventRecord(c->ev_stage[k], c->stream));
   const double *dd = (const double *)c->d_tables;
   const float *df = (const float *)((const char *)c->d_tables + n_dbl * sizeof(double));
   d.logkarr = dd + o_logk; d.pkarr = dd + o_pk;
@@ -142,6 +149,70 @@ static int upload_tables(gh_cuda_ctx *c, const gh_cuda_params *p)
   d.nu0 = dd + o_nu0; d.nuf = dd + o_nuf;
   d.z_r2z_f = df; d.gd_f = df + nz; d.gv_f = df + 2 * nz; d.nu_edges_f = df + 3 * nz; d.r_z2r_f = df + 3 * nz + nn + 1;
   d.inv_dz_tab = (float)(1.0 / p->dz_tab); d.z_tab_max = (float)p->z_arr_z2r[nz - 1];
+  return 0;
+}
+
+// per-shell prefactors through the tail of the same staging buffer (call after upload_tables)
+static int upload_prefac(gh_cuda_ctx *c)
+{
+  const int k = c->stage_cur;
+  char *h = c->h_stage[k] + c->tables_bytes;
+  memcpy(h, c->h_prefac, sizeof(double) * c->d.n_nu_pad);
+  GH_CUDA_OK(cudaMemcpyAsync(c->d_prefac, h, sizeof(double) * c->d.n_nu_pad, cudaMemcpyHostToDevice, c->stream));
+  GH_CUDA_OK(cudaEventRecord(c->ev_stage[k], c->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ map-plane load balance
+// mk_T_maps' cost per cell is far from uniform: cells outside the shells' radial window are dropped after a short
+// test, the others run ten sub-particles through the pixelisation.  With equal z slabs the ranks holding the box's
+// centre planes therefore work ~2.4x longer than the edge ranks (measured, 8 x B200, 2048^3).  The accumulation
+// is re-partitioned into contiguous plane ranges of equal modelled cost; a rank whose range reaches outside its
+// own slab pulls those planes' HI mass and Delta z_RSD from the owner over NVLink (enqueue_maps).
+// Cost model per plane: 0.18 + 0.82 * (fraction of the plane's cells with r_lo - h < r < r_hi + h), the weights
+// fitted to the per-slab times measured on 4 and 8 GPUs; the fraction is computed from the exact x-extent of
+// the annulus on a sample of rows.  Pure host code; every rank computes the same bounds.
+extern "C" int gh_cuda_map_plane_bounds(const gh_cuda_params *p, int nranks, int *bounds)
+{
+  GH_REQUIRE(p && bounds && nranks >= 1 && nranks <= GH_MAX_RANKS && p->n_grid > 0 && p->n_grid % nranks == 0,
+             "gh_cuda_map_plane_bounds: bad arguments");
+  const int n = p->n_grid;
+  const double dx = p->l_box / n, h = 0.8660254 * dx;
+  double nu_lo, nu_hi;
+  if (p->irregular_nutable) { nu_lo = p->nu0_arr[0]; nu_hi = p->nuf_arr[p->n_nu - 1]; }
+  else { nu_lo = p->nu_min - (p->nu_max - p->nu_min) / p->n_nu; nu_hi = p->nu_max; }
+  const double r_lo = fmax(0.0, host_r_of_z(p, GH_CUDA_NU_21 / nu_hi - 1) - h);
+  const double r_hi = host_r_of_z(p, GH_CUDA_NU_21 / nu_lo - 1) + h;
+  const double xmin = -p->pos_obs[0], xmax = p->l_box - p->pos_obs[0];
+  auto overlap = [&](double a, double b) { const double lo = a > xmin ? a : xmin, hi = b < xmax ? b : xmax; return hi > lo ? hi - lo : 0.0; };
+  const int stride = n > 256 ? n / 256 : 1;
+  double *w = (double *)malloc(sizeof(double) * (size_t)(n + 1));
+  GH_REQUIRE(w, "out of host memory");
+  w[0] = 0;
+  for (int z = 0; z < n; ++z) {
+    const double zc = dx * (z + 0.5) - p->pos_obs[2];
+    double len = 0;
+    int rows = 0;
+    for (int y = stride / 2; y < n; y += stride, ++rows) {
+      const double yc = dx * (y + 0.5) - p->pos_obs[1];
+      const double rho2 = yc * yc + zc * zc, b2 = r_hi * r_hi - rho2;
+      if (b2 <= 0) continue;
+      const double b = sqrt(b2), a = r_lo * r_lo > rho2 ? sqrt(r_lo * r_lo - rho2) : 0.0;
+      len += overlap(a, b) + overlap(-b, -a);
+    }
+    w[z + 1] = w[z] + 0.18 + 0.82 * len / (p->l_box * (rows > 0 ? rows : 1));
+  }
+  bounds[0] = 0;
+  int z = 0;
+  for (int r = 1; r < nranks; ++r) {
+    const double target = w[n] * r / nranks;
+    while (z < n && w[z] < target) ++z;
+    // the plane boundary closest to the target
+    if (z > bounds[r - 1] && target - w[z - 1] < w[z] - target) --z;
+    bounds[r] = z;
+  }
+  bounds[nranks] = n;
+  free(w);
   return 0;
 }
 
@@ -197,7 +268,19 @@ static int apply_params(gh_cuda_ctx *c, const gh_cuda_params *p, int rank, int n
       c->h_prefac[inu] = m2t / (r * r * dnu);
     }
   }
-
+  if (nranks > 1) {
+    if (gh_cuda_map_plane_bounds(p, nranks, c->map_bounds)) return 1;
+    if (const char *ov = getenv("GH_MAP_BOUNDS")) {  // test hook: "b1,b2,...": interior bounds, planes
+      int prev = 0;
+      for (int r = 1; r < nranks && ov && *ov; ++r) {
+        int v = atoi(ov);
+        v = v < prev ? prev : v > d.n ? d.n : v;
+        c->map_bounds[r] = prev = v;
+        ov = strchr(ov, ',');
+        if (ov) ++ov;
+      }
+    }
+  }
   return 0;
 }
 
@@ -268,8 +351,7 @@ static int setup_peers(gh_cuda_ctx *c)
     return 0;
   }
   c->have_peers = getenv("GH_NO_PEER") == nullptr;
-  // opt-in: see accumulate_kernel (measured: no net gain on 4 GPUs)
-  c->balance_maps = c->have_peers && P >= 4 && c->d.nz_here % (16 * P) == 0 && getenv("GH_BALANCE_MAPS") != nullptr;
+  c->rebalance = c->have_peers && getenv("GH_NO_REBALANCE") == nullptr;
   return 0;
 }
 
@@ -292,13 +374,22 @@ extern "C" int gh_cuda_destroy(gh_cuda_ctx *c)
   if (c->have_comm) ncclCommDestroy(c->comm);
   cudaFree(c->gridA); cudaFree(c->gridB); cudaFree(c->gridC);
   cudaFree(c->halo_lo); cudaFree(c->halo_hi);
-  cudaFree(c->maps); cudaFree(c->maps_recv);
+  for (int b = 0; b < 2; ++b) {
+    if (c->out_buf[b]) cudaFree(c->out_buf[b]);
+    if (c->ev_copied[b]) cudaEventDestroy(c->ev_copied[b]);
+    if (c->h_stage[b]) cudaFreeHost(c->h_stage[b]);
+    if (c->ev_stage[b]) cudaEventDestroy(c->ev_stage[b]);
+  }
+  if (c->maps != c->out_buf[0] && c->maps != c->out_buf[1]) cudaFree(c->maps);  // one rank: maps is one of out_buf[]
   cudaFree(c->twiddle); cudaFree(c->d_partials); cudaFree(c->d_prefac); cudaFree(c->d_tables);
   for (int i = 0; i < 2 * GH_T_NSLOTS; ++i)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  if (c->pull_stream) { cudaStreamSynchronize(c->pull_stream); cudaStreamDestroy(c->pull_stream); }
+  if (c->ev_bar) cudaEventDestroy(c->ev_bar);
+  if (c->ev_pulled) cudaEventDestroy(c->ev_pulled);
+  if (c->ev_chunk_free) cudaEventDestroy(c->ev_chunk_free);
   if (c->ev_done) cudaEventDestroy(c->ev_done);
-  if (c->ev_copied) cudaEventDestroy(c->ev_copied);
   if (c->h_stats) cudaFreeHost(c->h_stats);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -361,9 +452,14 @@ extern "C" int gh_cuda_create(const gh_cuda_params *p, int rank, int nranks, con
 
   CREATE_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CREATE_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CREATE_OK(cudaStreamCreateWithFlags(&c->pull_stream, cudaStreamNonBlocking));
+  CREATE_OK(cudaEventCreateWithFlags(&c->ev_bar, cudaEventDisableTiming));
+  CREATE_OK(cudaEventCreateWithFlags(&c->ev_pulled, cudaEventDisableTiming));
+  CREATE_OK(cudaEventCreateWithFlags(&c->ev_chunk_free, cudaEventDisableTiming));
   CREATE_OK(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
-  CREATE_OK(cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming));
-  CREATE_OK(cudaMallocHost((void **)&c->h_stats, 4 * sizeof(double)));
+  for (int b = 0; b < 2; ++b) CREATE_OK(cudaEventCreateWithFlags(&c->ev_copied[b], cudaEventDisableTiming));
+  CREATE_OK(cudaHostAlloc((void **)&c->h_stats, 4 * sizeof(double), cudaHostAllocMapped));
+  CREATE_OK(cudaHostGetDevicePointer((void **)&c->h_stats_dev, c->h_stats, 0));
   for (int i = 0; i < 2 * GH_T_NSLOTS; ++i) CREATE_OK(cudaEventCreate(&c->ev[i]));
   if (upload_tables(c, p)) { gh_cuda_destroy(c); return 1; }
 
@@ -375,15 +471,33 @@ extern "C" int gh_cuda_create(const gh_cuda_params *p, int rank, int nranks, con
   const size_t map_bytes = (size_t)d.n_nu_pad * d.npix * sizeof(float);
   CREATE_OK(cudaMalloc(&c->maps, map_bytes));
   CREATE_OK(cudaMemsetAsync(c->maps, 0, map_bytes, c->stream));
+  // out_buf[]: what the device->host copy reads -- the stack itself on one rank, the reduce-scatter output on
+  // several.  A second copy of it (when it fits comfortably) lets realisation i+1 write its result while the copy
+  // of realisation i is still on the wire.
+  size_t out_bytes = map_bytes;
   if (nranks > 1) {
     const size_t plane_bytes = (size_t)2 * d.nh * d.n * sizeof(float);
     CREATE_OK(cudaMalloc(&c->halo_lo, plane_bytes));
     CREATE_OK(cudaMalloc(&c->halo_hi, plane_bytes));
-    CREATE_OK(cudaMalloc(&c->maps_recv, (size_t)shells_per_rank * d.npix * sizeof(float)));
+    out_bytes = (size_t)shells_per_rank * d.npix * sizeof(float);
+    CREATE_OK(cudaMalloc(&c->out_buf[0], out_bytes));
+    c->maps_recv = c->out_buf[0];
+  } else {
+    c->out_buf[0] = c->maps;
+  }
+  {
+    size_t free_b = 0, total_b = 0;
+    CREATE_OK(cudaMemGetInfo(&free_b, &total_b));
+    const bool want = !getenv("GH_SINGLE_OUT") && free_b > out_bytes && free_b - out_bytes > total_b / 8;
+    if (want && cudaMalloc(&c->out_buf[1], out_bytes) != cudaSuccess) {
+      c->out_buf[1] = nullptr;
+      (void)cudaGetLastError();
+    }
+    if (c->out_buf[1] && nranks == 1) CREATE_OK(cudaMemsetAsync(c->out_buf[1], 0, out_bytes, c->stream));
   }
   CREATE_OK(cudaMalloc(&c->d_partials, sizeof(double) * (8 + 2 * ((size_t)c->n_sm * 8 + (size_t)d.nz_here * d.n))));
   CREATE_OK(cudaMalloc(&c->d_prefac, sizeof(double) * d.n_nu_pad));
-  CREATE_OK(cudaMemcpyAsync(c->d_prefac, c->h_prefac, sizeof(double) * d.n_nu_pad, cudaMemcpyHostToDevice, c->stream));
+  if (upload_prefac(c)) { gh_cuda_destroy(c); return 1; }
   {
     float2 *tw = (float2 *)malloc(sizeof(float2) * d.n);
     if (!tw) { gh_cuda_destroy(c); gh_set_error("out of host memory"); return 1; }
@@ -428,8 +542,7 @@ extern "C" int gh_cuda_set_params(gh_cuda_ctx *c, const gh_cuda_params *p)
              "gh_cuda_set_params: missing table pointer");
   if (apply_params(c, p, c->d.rank, c->d.nranks)) return 1;
   if (upload_tables(c, p)) return 1;
-  GH_CUDA_OK(cudaMemcpyAsync(c->d_prefac, c->h_prefac, sizeof(double) * c->d.n_nu_pad, cudaMemcpyHostToDevice, c->stream));
-  GH_CUDA_OK(cudaStreamSynchronize(c->stream));
+  if (upload_prefac(c)) return 1;
   c->sigma_overridden = false;
   return 0;
 }
@@ -513,10 +626,6 @@ static int enqueue_sigma(gh_cuda_ctx *c)
   if (gh_launch_sigma(c)) return 1;
   if (c->d.nranks > 1) GH_NCCL_OK(ncclAllReduce(c->d_partials, c->d_partials, 2, ncclDouble, ncclSum, c->comm, c->stream));
   if (gh_launch_sigma_finish(c)) return 1;
-  GH_CUDA_OK(cudaMemcpyAsync(c->h_stats, c->d_partials, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  GH_CUDA_OK(cudaMemcpyAsync(c->h_stats + 2, c->d_partials + 4, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  if (c->sigma_overridden)  // a caller-supplied sigma2_gauss wins over the measured one
-    GH_CUDA_OK(cudaMemcpyAsync(c->d_partials + 5, &c->sigma2_gauss, sizeof(double), cudaMemcpyHostToDevice, c->stream));
   c->sigma_ready = true;
   return 0;
 }
@@ -554,9 +663,68 @@ extern "C" int gh_cuda_get_HI(gh_cuda_ctx *c)
 extern "C" int gh_cuda_zero_maps(gh_cuda_ctx *c)
 {
   GH_CTX(c);
-  // a device->host copy of the previous realisation's maps may still be reading them
-  if (c->copy_pending) GH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_copied, 0));
+  // one rank: a device->host copy of an earlier realisation may still be reading this buffer (several ranks:
+  // copies read the reduce-scatter output, never the accumulation stack)
+  if (c->d.nranks == 1 && c->copy_pending[c->out_cur]) GH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_copied[c->out_cur], 0));
   GH_CUDA_OK(cudaMemsetAsync(c->maps, 0, (size_t)c->d.n_nu_pad * c->d.npix * sizeof(float), c->stream));
+  return 0;
+}
+
+static int accumulate_own_slab(gh_cuda_ctx *c)
+{
+  return gh_launch_accumulate(c, reinterpret_cast<const float *>(c->gridA), reinterpret_cast<const float *>(c->gridC), 0, c->d.iz0,
+                              c->d.nz_here);
+}
+
+// Several ranks with peer mappings: accumulate the plane range [map_bounds[rank], map_bounds[rank+1]) instead of
+// the own slab.  Planes of the range that live on other ranks are copied (HI mass and Delta z_RSD, 8 B/cell) into
+// the vpot slab, which is free by now, on the pull stream while the own planes are being accumulated.
+// Ordering: the all-reduce barrier says every rank's get_HI has finished before anybody pulls; the reduce-scatter
+// that follows the accumulation cannot complete anywhere before every rank has finished pulling, so no rank
+// starts overwriting its slabs (next realisation) under a reader.
+static int accumulate_rebalanced(gh_cuda_ctx *c)
+{
+  const GhDev &d = c->d;
+  const int lo = c->map_bounds[d.rank], hi = c->map_bounds[d.rank + 1];
+  const int o0 = d.iz0, o1 = d.iz0 + d.nz_here;
+  const size_t plane = (size_t)d.n * 2 * d.nh;  // floats
+  const float *own_m = reinterpret_cast<const float *>(c->gridA), *own_z = reinterpret_cast<const float *>(c->gridC);
+  float *stage_m = reinterpret_cast<float *>(c->gridB);
+  const int cap = d.nz_here / 2;                // planes of (mass, dz) pairs the vpot slab can stage
+  float *stage_z = stage_m + (size_t)cap * plane;
+  if (gh_stream_barrier(c)) return 1;
+  GH_CUDA_OK(cudaEventRecord(c->ev_bar, c->stream));
+  GH_CUDA_OK(cudaStreamWaitEvent(c->pull_stream, c->ev_bar, 0));
+  const int foreign[2][2] = {{lo, hi < o0 ? hi : o0}, {lo > o1 ? lo : o1, hi}};
+  // first chunk of pulls goes out before the own planes are launched, so the two overlap
+  bool own_done = false, first = true;
+  for (int f = 0; f < 2; ++f) {
+    for (int z0 = foreign[f][0]; z0 < foreign[f][1]; z0 += cap) {
+      const int z1 = z0 + cap < foreign[f][1] ? z0 + cap : foreign[f][1];
+      if (!first) GH_CUDA_OK(cudaStreamWaitEvent(c->pull_stream, c->ev_chunk_free, 0));
+      for (int z = z0; z < z1;) {  // one copy pair per owner
+        const int q = z / d.nz_here, zq1 = (q + 1) * d.nz_here < z1 ? (q + 1) * d.nz_here : z1;
+        const size_t src = (size_t)(z - q * d.nz_here) * plane, dst = (size_t)(z - z0) * plane, bytes = (size_t)(zq1 - z) * plane * sizeof(float);
+        GH_CUDA_OK(cudaMemcpyAsync(stage_m + dst, reinterpret_cast<const float *>(c->peers.A[q]) + src, bytes, cudaMemcpyDefault, c->pull_stream));
+        GH_CUDA_OK(cudaMemcpyAsync(stage_z + dst, reinterpret_cast<const float *>(c->peers.C[q]) + src, bytes, cudaMemcpyDefault, c->pull_stream));
+        z = zq1;
+      }
+      GH_CUDA_OK(cudaEventRecord(c->ev_pulled, c->pull_stream));
+      if (!own_done) {
+        const int a = lo > o0 ? lo : o0, b = hi < o1 ? hi : o1;
+        if (gh_launch_accumulate(c, own_m, own_z, a - o0, a, b - a)) return 1;
+        own_done = true;
+      }
+      GH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_pulled, 0));
+      if (gh_launch_accumulate(c, stage_m, stage_z, 0, z0, z1 - z0)) return 1;
+      GH_CUDA_OK(cudaEventRecord(c->ev_chunk_free, c->stream));
+      first = false;
+    }
+  }
+  if (!own_done) {
+    const int a = lo > o0 ? lo : o0, b = hi < o1 ? hi : o1;
+    if (gh_launch_accumulate(c, own_m, own_z, a - o0, a, b - a)) return 1;
+  }
   return 0;
 }
 
@@ -564,7 +732,7 @@ extern "C" int gh_cuda_accumulate_maps(gh_cuda_ctx *c)
 {
   GH_CTX(c);
   StageTimer t(c, GH_T_MAPS);
-  return gh_launch_accumulate(c);
+  return accumulate_own_slab(c);
 }
 
 // accumulate -> (reduce-scatter) -> scale -> device->host copy on the copy stream; no host synchronisation
@@ -573,28 +741,34 @@ static int enqueue_maps(gh_cuda_ctx *c, float *maps_host)
   const GhDev &d = c->d;
   int n_here = 0, s0 = 0;
   gh_cuda_shells(c, &n_here, &s0);
-  float *result = c->maps;
+  if (c->out_buf[1]) {  // write this realisation's result into the buffer the last copy is not reading
+    c->out_cur ^= 1;
+    if (d.nranks == 1) c->maps = c->out_buf[c->out_cur];
+    else c->maps_recv = c->out_buf[c->out_cur];
+  }
+  const int cur = c->out_cur;
   if (d.nranks == 1) {
     StageTimer t(c, GH_T_MAPS);
     if (gh_cuda_zero_maps(c)) return 1;
-    if (gh_launch_accumulate(c)) return 1;
+    if (accumulate_own_slab(c)) return 1;
     if (gh_launch_scale_maps(c, c->maps, 0, d.n_nu)) return 1;
   } else {
     {
       StageTimer t(c, GH_T_MAPS);
       if (gh_cuda_zero_maps(c)) return 1;
-      if (gh_launch_accumulate(c)) return 1;
+      if ((c->rebalance && d.nz_here >= 2) ? accumulate_rebalanced(c) : accumulate_own_slab(c)) return 1;
     }
     {
       // the reference sums full per-rank stacks onto rank 0 (src/pixelize.c:266-284); here every rank ends
       // up with the sum of its own shells, then scales just those
       StageTimer t(c, GH_T_REDUCE);
       const size_t per = (size_t)(d.n_nu_pad / d.nranks) * d.npix;
+      if (c->copy_pending[cur]) GH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_copied[cur], 0));
       GH_NCCL_OK(ncclReduceScatter(c->maps, c->maps_recv, per, ncclFloat, ncclSum, c->comm, c->stream));
       if (gh_launch_scale_maps(c, c->maps_recv, s0, n_here)) return 1;
     }
-    result = c->maps_recv;
   }
+  float *result = c->out_buf[cur];
   if (maps_host && n_here > 0) {
     GH_CUDA_OK(cudaEventRecord(c->ev_done, c->stream));
     GH_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_done, 0));
@@ -602,8 +776,8 @@ static int enqueue_maps(gh_cuda_ctx *c, float *maps_host)
     GH_CUDA_OK(cudaMemcpyAsync(maps_host, result, (size_t)n_here * d.npix * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
     GH_CUDA_OK(cudaEventRecord(c->ev[2 * GH_T_D2H + 1], c->copy_stream));
     c->ev_used[GH_T_D2H] = true;
-    GH_CUDA_OK(cudaEventRecord(c->ev_copied, c->copy_stream));
-    c->copy_pending = true;
+    GH_CUDA_OK(cudaEventRecord(c->ev_copied[cur], c->copy_stream));
+    c->copy_pending[cur] = true;
   }
   return 0;
 }
@@ -612,8 +786,10 @@ extern "C" int gh_cuda_wait(gh_cuda_ctx *c, double *sigma2_out)
 {
   GH_CTX(c);
   GH_CUDA_OK(cudaStreamSynchronize(c->stream));
-  if (c->copy_pending) GH_CUDA_OK(cudaEventSynchronize(c->ev_copied));
-  c->copy_pending = false;
+  for (int b = 0; b < 2; ++b) {
+    if (c->copy_pending[b]) GH_CUDA_OK(cudaEventSynchronize(c->ev_copied[b]));
+    c->copy_pending[b] = false;
+  }
   if (c->sigma_ready) {
     c->mean_gauss = c->h_stats[2];
     if (!c->sigma_overridden) c->sigma2_gauss = c->h_stats[3];

@@ -119,11 +119,19 @@ __global__ void __launch_bounds__(256) sigma_final_kernel(double *__restrict__ p
 }
 
 // mean and variance from the (all-reduced) sums: partials[4] = <d>, partials[5] = <d^2> - <d>^2 (src/fourier.c:59-74)
-__global__ void sigma_finish_kernel(double *__restrict__ partials, double inv_ng_tot)
+// The four numbers the host wants (sum, sum of squares, mean, variance) are stored straight into mapped pinned
+// host memory: a cudaMemcpyAsync here would queue behind the previous realisation's 200 MB map download on the
+// device->host copy engine and stall the compute stream for ~1 ms (measured).  A caller-supplied sigma2_gauss
+// (gh_cuda_set_sigma2_gauss) replaces the measured variance for get_HI.
+__global__ void sigma_finish_kernel(double *__restrict__ partials, double inv_ng_tot, double *__restrict__ host_stats,
+                                    int overridden, double sigma2_override)
 {
-  const double mean = partials[0] * inv_ng_tot;
+  const double sum = partials[0], sumsq = partials[1];
+  const double mean = sum * inv_ng_tot, var = sumsq * inv_ng_tot - mean * mean;
   partials[4] = mean;
-  partials[5] = partials[1] * inv_ng_tot - mean * mean;
+  partials[5] = overridden ? sigma2_override : var;
+  host_stats[0] = sum; host_stats[1] = sumsq; host_stats[2] = mean; host_stats[3] = var;
+  __threadfence_system();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -205,7 +213,7 @@ int gh_launch_sigma(gh_cuda_ctx *c)
 int gh_launch_sigma_finish(gh_cuda_ctx *c)
 {
   const double ng_tot = (double)c->d.n * ((double)c->d.n * (double)c->d.n);
-  sigma_finish_kernel<<<1, 1, 0, c->stream>>>(c->d_partials, 1.0 / ng_tot);
+  sigma_finish_kernel<<<1, 1, 0, c->stream>>>(c->d_partials, 1.0 / ng_tot, c->h_stats_dev, c->sigma_overridden ? 1 : 0, c->sigma2_gauss);
   GH_LAUNCH_CHECK(c);
   return 0;
 }

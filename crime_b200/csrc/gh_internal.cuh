@@ -56,20 +56,29 @@ struct gh_cuda_ctx {
   int device;
   cudaStream_t stream;
   cudaStream_t copy_stream;        // device->host copy of the finished maps, overlaps the next realisation
-  cudaEvent_t ev_done, ev_copied;
-  bool copy_pending, sigma_ready;
-  double *h_stats;                 // pinned: sum, sumsq, mean, sigma2 of the last realisation
+  cudaEvent_t ev_done, ev_copied[2];
+  bool copy_pending[2], sigma_ready;
+  float *out_buf[2];               // what the device->host copy reads (maps on one rank, maps_recv on several), doubled when it fits
+  int out_cur;
+  char *h_stage[2];                // pinned staging of the tables + prefactors, used alternately
+  cudaEvent_t ev_stage[2];
+  int stage_next, stage_cur;
+  double *h_stats;                 // mapped pinned: sum, sumsq, mean, sigma2 of the last realisation (written by the kernel)
+  double *h_stats_dev;             // its device-side address
   ncclComm_t comm;
   bool have_comm;
   bool have_peers;                 // peer mappings established (nranks>1, same node)
-  bool balance_maps;               // deal map planes round-robin across ranks (peer reads)
+  bool rebalance;                  // accumulate equal-cost plane ranges, pulling foreign planes from peers
+  int map_bounds[GH_MAX_RANKS + 1];
+  cudaStream_t pull_stream;
+  cudaEvent_t ev_bar, ev_pulled, ev_chunk_free;
   GhPeers peers;
   int *d_barrier;                  // one int, all-reduced as a stream-ordered cross-rank barrier
   size_t slab_complex;  // complex elements per slab = nz_here*n*nh (== n*nky_here*nh)
   float2 *gridA, *gridB, *gridC;  // dens, vpot, rvel/transposition scratch
   float *halo_lo, *halo_hi;       // neighbour planes of vpot (nranks>1)
-  float *maps;                    // [n_nu_pad][npix]
-  float *maps_recv;               // reduce-scatter output (nranks>1)
+  float *maps;                    // [n_nu_pad][npix] accumulation stack (== out_buf[out_cur] on one rank)
+  float *maps_recv;               // reduce-scatter output (nranks>1) == out_buf[out_cur]
   float2 *twiddle;                // exp(+2 pi i j/n), j<n
   double *d_partials;             // reduction scratch
   double *d_prefac;               // per-shell mass->temperature factors
@@ -125,7 +134,7 @@ int gh_launch_radial_velocity(gh_cuda_ctx *c);
 int gh_launch_sigma(gh_cuda_ctx *c);  // leaves (sum, sumsq) in c->d_partials[0..1]
 int gh_launch_sigma_finish(gh_cuda_ctx *c);  // d_partials[4] = mean, [5] = sigma2_gauss
 int gh_launch_get_HI(gh_cuda_ctx *c);
-int gh_launch_accumulate(gh_cuda_ctx *c);
+int gh_launch_accumulate(gh_cuda_ctx *c, const float *mass, const float *dzrsd, int iz_base, int zg_base, int nplanes);
 int gh_stream_barrier(gh_cuda_ctx *c);  // every rank has reached this point of its stream
 int gh_launch_accumulate_audit(gh_cuda_ctx *c, float eps_scale, unsigned long long *d_counts);
 int gh_launch_scale_maps(gh_cuda_ctx *c, float *maps, int shell0, int nshells);

@@ -214,17 +214,14 @@ __device__ __forceinline__ bool fast_pixel(const FastCtx &f, float cth, float tt
 // into a shared-memory queue and re-does exactly those in fp64 (gh_point_to_shell_pixel) on as few warps
 // as possible.
 // AUDIT: nothing is deposited; every sub-particle is evaluated by both paths and the outcomes counted.
-// BALANCED (opt-in, GH_BALANCE_MAPS=1, nranks >= 4): slabs near the box centre hold more in-range cells than
-// edge slabs; in this mode the planes are dealt round-robin instead: this rank takes global planes
-// z = k*P + rank and reads the HI mass and Delta z_RSD of planes it does not own straight from the owner's
-// memory over NVLink.  Measured on 4 x B200 (1024^3) it evens the ranks out at the cost of the slowest slab
-// (every rank then scatters over the whole sky instead of its own part of it), so it is off by default.
-#define GH_BAL_BLOCK 16
-template <bool AUDIT, bool BALANCED>
+// Planes: the launch covers gridDim.z consecutive planes; plane blockIdx.z sits at local index iz_base +
+// blockIdx.z of the buffers passed in and is global plane zg_base + blockIdx.z (this rank's own slab, or planes
+// pulled from a neighbour for load balance -- see enqueue_maps in gh_api.cu).
+template <bool AUDIT>
 __global__ void __launch_bounds__(128) accumulate_kernel(GhDev d, const float *__restrict__ mass,
                                                          const float *__restrict__ dzrsd, float *__restrict__ maps,
                                                          float eps_scale, unsigned long long *__restrict__ counts,
-                                                         GhPeers peers)
+                                                         int iz_base, int zg_base)
 {
   __shared__ unsigned short queue[128 * GH_CUDA_N_SUBPART];
   __shared__ float s_dz[128], s_w[128];
@@ -233,20 +230,7 @@ __global__ void __launch_bounds__(128) accumulate_kernel(GhDev d, const float *_
   const int tid = threadIdx.x + 8 * threadIdx.y;  // blockDim = (8, 16)
   if (!AUDIT && tid == 0) s_count = 0;
   const int ix = blockIdx.x * 8 + threadIdx.x, iy = blockIdx.y * 16 + threadIdx.y;
-  int iz = blockIdx.z, zg = blockIdx.z + d.iz0;  // local plane in the owner's slab, global plane
-  if (BALANCED) {
-    // planes are dealt in blocks of GH_BAL_BLOCK consecutive planes (consecutive planes deposit into nearly the
-    // same pixels, which keeps the atomics' sectors L2-resident), block-cyclically over the ranks, each rank
-    // starting its sweep at its own slab so that at any moment every rank reads from a different owner
-    const int nblk = d.nz_here / GH_BAL_BLOCK;                      // blocks per rank
-    const int jb = (int)blockIdx.z / GH_BAL_BLOCK, jo = (int)blockIdx.z % GH_BAL_BLOCK;
-    const int kb = (jb + d.rank * (nblk / d.nranks)) % nblk;        // rotated block counter
-    zg = (kb * d.nranks + d.rank) * GH_BAL_BLOCK + jo;
-    const int owner = zg / d.nz_here;
-    iz = zg - owner * d.nz_here;
-    mass = reinterpret_cast<const float *>(peers.A[owner]);
-    dzrsd = reinterpret_cast<const float *>(peers.C[owner]);
-  }
+  const int iz = blockIdx.z + iz_base, zg = blockIdx.z + zg_base;
   const bool active = (ix < d.n) && (iy < d.n);
   const FastCtx f = fast_ctx_of(d, eps_scale);
   const GhIndexTables t = tables_of(d);
@@ -258,7 +242,6 @@ __global__ void __launch_bounds__(128) accumulate_kernel(GhDev d, const float *_
   unsigned long long c_out = 0, c_in = 0, c_unsure = 0, c_wrong = 0;
   if (active) {
     const size_t idx = ((size_t)iz * d.n + iy) * ngx + ix;
-    // both loads up front (they may come from a peer GPU: one NVLink round trip, not two)
     const float cell_mass = __ldcs(mass + idx);
     dzf = __ldcs(dzrsd + idx);
     // cell centre as hi + lo floats: positions are xh + (xl + offset), one rounding of the full coordinate
@@ -436,18 +419,12 @@ __global__ void __launch_bounds__(128) points_kernel(GhDev d, const double *__re
 
 }  // namespace
 
-int gh_launch_accumulate(gh_cuda_ctx *c)
+int gh_launch_accumulate(gh_cuda_ctx *c, const float *mass, const float *dzrsd, int iz_base, int zg_base, int nplanes)
 {
   const GhDev &d = c->d;
-  dim3 grid((d.n + 7) / 8, (d.n + 15) / 16, d.nz_here), block(8, 16);
-  if (d.nranks > 1 && c->have_peers && c->balance_maps) {
-    // every rank's get_HI must have landed before anybody reads its slab
-    if (gh_stream_barrier(c)) return 1;
-    accumulate_kernel<false, true><<<grid, block, 0, c->stream>>>(d, nullptr, nullptr, c->maps, 1.0f, nullptr, c->peers);
-  } else {
-    accumulate_kernel<false, false><<<grid, block, 0, c->stream>>>(d, reinterpret_cast<const float *>(c->gridA),
-                                                                 reinterpret_cast<const float *>(c->gridC), c->maps, 1.0f, nullptr, c->peers);
-  }
+  if (nplanes <= 0) return 0;
+  dim3 grid((d.n + 7) / 8, (d.n + 15) / 16, nplanes), block(8, 16);
+  accumulate_kernel<false><<<grid, block, 0, c->stream>>>(d, mass, dzrsd, c->maps, 1.0f, nullptr, iz_base, zg_base);
   GH_LAUNCH_CHECK(c);
   return 0;
 }
@@ -456,8 +433,8 @@ int gh_launch_accumulate_audit(gh_cuda_ctx *c, float eps_scale, unsigned long lo
 {
   const GhDev &d = c->d;
   dim3 grid((d.n + 7) / 8, (d.n + 15) / 16, d.nz_here), block(8, 16);
-  accumulate_kernel<true, false><<<grid, block, 0, c->stream>>>(d, reinterpret_cast<const float *>(c->gridA),
-                                                              reinterpret_cast<const float *>(c->gridC), c->maps, eps_scale, d_counts, c->peers);
+  accumulate_kernel<true><<<grid, block, 0, c->stream>>>(d, reinterpret_cast<const float *>(c->gridA),
+                                                       reinterpret_cast<const float *>(c->gridC), c->maps, eps_scale, d_counts, 0, d.iz0);
   GH_LAUNCH_CHECK(c);
   return 0;
 }

@@ -35,3 +35,15 @@ def received_index(n_grid: int, nranks: int, z_local: int, ky: int, kx: int) -> 
     nh = n_grid // 2 + 1
     q, j = divmod(ky, nyl)
     return q * transpose_chunk(n_grid, nranks) + (z_local * nyl + j) * nh + kx
+
+
+def map_plane_ranges(params, nranks: int) -> list[tuple[int, int]]:
+    """[(first, last+1)] plane range each rank accumulates in mk_T_maps (gh_cuda_map_plane_bounds): equal modelled
+    cost instead of equal plane counts.  Host-only; needs the built library but no GPU."""
+    import ctypes as C
+    from . import abi
+    lib = abi.load_library()
+    b = (C.c_int * (nranks + 1))()
+    if lib.gh_cuda_map_plane_bounds(C.byref(params), nranks, b):
+        raise RuntimeError(lib.gh_cuda_last_error().decode())
+    return [(b[r], b[r + 1]) for r in range(nranks)]

@@ -114,6 +114,12 @@ int gh_cuda_destroy(gh_cuda_ctx *ctx);
 int gh_cuda_slab(const gh_cuda_ctx *ctx, int *nz_here, int *iz0_here);
 int gh_cuda_shells(const gh_cuda_ctx *ctx, int *n_shells_here, int *shell0_here);
 
+/* Plane ranges of the map accumulation on nranks GPUs: rank r accumulates planes [bounds[r], bounds[r+1])
+ * (bounds has nranks+1 entries).  The reference gives every rank its own slab (src/pixelize.c:186-232); its
+ * cells' cost is uneven (cells outside the shells' radial window are skipped), so the ranges are chosen for equal
+ * modelled cost and a rank pulls planes outside its slab from the owner over NVLink.  Host-only, no GPU needed. */
+int gh_cuda_map_plane_bounds(const gh_cuda_params *params, int nranks, int *bounds);
+
 /* == create_d_and_vr_fields (src/fourier.c:375-438): k-space realisation, two c2r FFTs, normalisation,
  * halo exchange, radial velocity, Gaussian variance.  *sigma2_gauss_out receives par->sigma2_gauss and
  * *mean_gauss_out (may be NULL) the <d> of the reference's log line (src/fourier.c:75).

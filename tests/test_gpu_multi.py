@@ -14,13 +14,23 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("world,n_grid,n_side", [(2, 64, 32), (4, 128, 64), (8, 128, 64)])
-def test_slab_decomposition_matches_single_gpu(world, n_grid, n_side):
+# bounds: GH_MAP_BOUNDS, forced plane ranges for the map accumulation (None = the cost model's; "off" = own slabs).
+# The forced cases make rank 0 pull planes from above, rank 1 from below, in more than one staging chunk, and
+# leave one rank without any of its own planes.
+@pytest.mark.parametrize("world,n_grid,n_side,bounds", [(2, 64, 32, None), (2, 64, 32, "57"), (2, 64, 32, "9"), (2, 64, 32, "off"),
+                                                        (4, 128, 64, None), (4, 128, 64, "70,75,80"), (8, 128, 64, None)])
+def test_slab_decomposition_matches_single_gpu(world, n_grid, n_side, bounds):
+    import os
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
+    env = dict(os.environ)
+    if bounds == "off":
+        env["GH_NO_REBALANCE"] = "1"
+    elif bounds:
+        env["GH_MAP_BOUNDS"] = bounds
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(29400 + world), str(ROOT / "tests" / "multi_gpu_worker.py"), str(n_grid), str(n_side)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert "MULTI_GPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
