@@ -46,6 +46,42 @@ def load_tables(n_nu: int) -> dict:
     return t
 
 
+def t_total_c_host(n_grid: int, n_side: int, n_nu: int) -> dict:
+    """T_total as the reference's own total timer brackets it (main_gh.c:42,69) -- `./GetHI file` from
+    param read through cosmology tables, device bring-up and the hot path to the last FITS map on disk (tmpfs),
+    with this repository's C host (host/GetHI): the maps are written while they are still being downloaded."""
+    import re
+    import shutil
+    import subprocess
+    import tempfile
+    exe = ROOT / "host" / "GetHI"
+    if not exe.exists():
+        return {"error": "host/GetHI not built"}
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    d = Path(tempfile.mkdtemp(prefix="gethi_ttotal_", dir=base))
+    try:
+        edges = np.linspace(355.0, 945.0, n_nu + 1)
+        (d / "nu.txt").write_text("".join(f"{e:.6f}\n" for e in edges))
+        (d / "p.ini").write_text(
+            f"prefix_out= {d}/map\npk_filename= {ROOT}/data/Pk_synth.dat\nomega_M= 0.3\nomega_L= 0.7\nomega_B= 0.049\nh= 0.67\n"
+            f"w= -1.0\nns= 0.96\nsigma_8= 0.8\nr_smooth= 2.0\nfrequencies_filename= {d}/nu.txt\nn_side= {n_side}\n"
+            f"n_grid= {n_grid}\nseed= 1001\ndo_psources= 0\n")
+        t0 = time.perf_counter()
+        r = subprocess.run([str(exe), str(d / "p.ini")], capture_output=True, text=True, timeout=600)
+        wall = time.perf_counter() - t0
+        if r.returncode != 0:
+            return {"error": (r.stdout + r.stderr)[-300:]}
+        m = re.search(r"Total time ellapsed ([0-9.]+) ms", r.stdout)
+        written = sum(f.stat().st_size for f in d.glob("map_*.fits"))
+        inside = float(m.group(1)) / 1e3 if m else None
+        return {"process_wall_s": round(wall, 3), "reference_total_timer_s": inside, "fits_bytes_written": written,
+                "mcells_per_s": (float(n_grid) ** 3 / inside / 1e6) if inside else None,
+                "what": "host/GetHI param file -> FITS maps on tmpfs: param read, cosmology tables, device bring-up, hot path, "
+                        f"{n_nu} maps written by the streaming writer"}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -205,6 +241,7 @@ def main():
     ap.add_argument("--shells", type=int, default=0)
     ap.add_argument("--cpu-grid", type=int, default=0, help="grid of the bounded CPU sample (default min(grid,256))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-t-total", action="store_true", help="skip the ./GetHI param-file-to-FITS run")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm (memory-capacity stress configs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -380,8 +417,14 @@ def main():
             except Exception as exc:  # the CPU arm must never take the GPU line down with it
                 line["cpu_baseline"] = {"value": None, "unit": "Mcells/s", "cores": os.cpu_count(), "kind": "port",
                                         "sample": f"failed: {exc}"}
-        print(json.dumps(line), flush=True)
     g.end_fftw()
+    if rank == 0:
+        if world == 1 and not args.no_t_total:
+            try:
+                line["t_total"] = t_total_c_host(n_grid, n_side, n_nu)
+            except Exception as exc:
+                line["t_total"] = {"error": str(exc)}
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier(device_ids=[local_rank])
         dist.destroy_process_group()

@@ -386,6 +386,8 @@ extern "C" int gh_cuda_destroy(gh_cuda_ctx *c)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   if (c->pull_stream) { cudaStreamSynchronize(c->pull_stream); cudaStreamDestroy(c->pull_stream); }
+  for (int i = 0; i < GH_MAX_CHUNKS; ++i)
+    if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
   if (c->ev_bar) cudaEventDestroy(c->ev_bar);
   if (c->ev_pulled) cudaEventDestroy(c->ev_pulled);
   if (c->ev_chunk_free) cudaEventDestroy(c->ev_chunk_free);
@@ -769,16 +771,50 @@ static int enqueue_maps(gh_cuda_ctx *c, float *maps_host)
     }
   }
   float *result = c->out_buf[cur];
+  c->n_chunks = 0;
   if (maps_host && n_here > 0) {
     GH_CUDA_OK(cudaEventRecord(c->ev_done, c->stream));
     GH_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_done, 0));
     GH_CUDA_OK(cudaEventRecord(c->ev[2 * GH_T_D2H], c->copy_stream));
-    GH_CUDA_OK(cudaMemcpyAsync(maps_host, result, (size_t)n_here * d.npix * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+    // the copy goes out in chunks of whole shells (>= 32 MiB, at most GH_MAX_CHUNKS of them), an event behind
+    // each, so that a consumer (the FITS writer) can start on the first shells while the rest is on the wire
+    const size_t shell_bytes = (size_t)d.npix * sizeof(float);
+    int per = (int)((((size_t)32 << 20) + shell_bytes - 1) / shell_bytes);
+    if (per * GH_MAX_CHUNKS < n_here) per = (n_here + GH_MAX_CHUNKS - 1) / GH_MAX_CHUNKS;
+    c->chunk_shells = per;
+    for (int s = 0; s < n_here; s += per) {
+      const int ns = s + per < n_here ? per : n_here - s;
+      GH_CUDA_OK(cudaMemcpyAsync(maps_host + (size_t)s * d.npix, result + (size_t)s * d.npix, (size_t)ns * shell_bytes,
+                                 cudaMemcpyDeviceToHost, c->copy_stream));
+      if (!c->ev_chunk[c->n_chunks]) GH_CUDA_OK(cudaEventCreateWithFlags(&c->ev_chunk[c->n_chunks], cudaEventDisableTiming));
+      GH_CUDA_OK(cudaEventRecord(c->ev_chunk[c->n_chunks], c->copy_stream));
+      c->n_chunks++;
+    }
     GH_CUDA_OK(cudaEventRecord(c->ev[2 * GH_T_D2H + 1], c->copy_stream));
     c->ev_used[GH_T_D2H] = true;
     GH_CUDA_OK(cudaEventRecord(c->ev_copied[cur], c->copy_stream));
     c->copy_pending[cur] = true;
   }
+  return 0;
+}
+
+extern "C" int gh_cuda_mk_T_maps_begin(gh_cuda_ctx *c, float *maps_host)
+{
+  GH_CTX(c);
+  GH_REQUIRE(maps_host, "gh_cuda_mk_T_maps_begin: null host buffer");
+  return enqueue_maps(c, maps_host);
+}
+
+extern "C" int gh_cuda_wait_shells(gh_cuda_ctx *c, int n_shells)
+{
+  GH_CTX(c);
+  int n_here = 0;
+  gh_cuda_shells(c, &n_here, nullptr);
+  if (n_shells < 0 || n_shells > n_here) n_shells = n_here;
+  if (n_shells == 0 || c->n_chunks == 0) return 0;
+  int idx = (n_shells + c->chunk_shells - 1) / c->chunk_shells - 1;
+  if (idx >= c->n_chunks) idx = c->n_chunks - 1;
+  GH_CUDA_OK(cudaEventSynchronize(c->ev_chunk[idx]));
   return 0;
 }
 

@@ -43,6 +43,7 @@ struct GhDev {
 };
 
 #define GH_MAX_RANKS 16
+#define GH_MAX_CHUNKS 64
 
 // Peer views of the slab buffers of every rank (CUDA IPC mappings; entry [rank] is the local buffer).
 // Kernels use them to read or write other GPUs' memory over NVLink directly.
@@ -63,6 +64,8 @@ struct gh_cuda_ctx {
   char *h_stage[2];                // pinned staging of the tables + prefactors, used alternately
   cudaEvent_t ev_stage[2];
   int stage_next, stage_cur;
+  cudaEvent_t ev_chunk[GH_MAX_CHUNKS];  // one behind every chunk of the last map download
+  int n_chunks, chunk_shells;
   double *h_stats;                 // mapped pinned: sum, sumsq, mean, sigma2 of the last realisation (written by the kernel)
   double *h_stats_dev;             // its device-side address
   ncclComm_t comm;

@@ -103,6 +103,17 @@ class GetHI:
         self.maps_HI = buf
         return buf
 
+    def mk_T_maps_begin(self, slot: int = 0) -> np.ndarray:
+        """Non-blocking mk_T_maps: the download of this rank's shells is queued in chunks of whole shells;
+        wait_shells(n) returns when the first n are complete in the returned buffer."""
+        buf = self._host_maps(slot)
+        self._check(self.lib.gh_cuda_mk_T_maps_begin(self._ctx, _ptr(buf)))
+        self.maps_HI = buf
+        return buf
+
+    def wait_shells(self, n_shells: int = -1) -> None:
+        self._check(self.lib.gh_cuda_wait_shells(self._ctx, n_shells))
+
     def end_fftw(self) -> None:
         """src/fourier.c:201 (+ the grid part of param_gethi_free, src/io_gh.c:298-324)."""
         if self._ctx:

@@ -52,6 +52,7 @@ typedef struct ParamGetHI {
   /* this rank's shells of the finished map stack, [n_shells_here][12 n_side^2], page-locked */
   float *maps_HI;
   int n_shells_here, shell0_here;
+  int maps_streaming; /* mk_T_maps_begin was called: write_maps waits shell by shell for the download */
   /* process layout: one process per GPU */
   int rank, nranks, device;
   gh_cuda_ctx *cuda;
@@ -85,6 +86,7 @@ void init_fftw(ParamGetHI *par);
 void create_d_and_vr_fields(ParamGetHI *par);
 void get_HI(ParamGetHI *par);
 void mk_T_maps(ParamGetHI *par);
+void mk_T_maps_begin(ParamGetHI *par); /* non-blocking form; write_maps then overlaps the download */
 void end_fftw(ParamGetHI *par);
 
 /* helpers */

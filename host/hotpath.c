@@ -79,6 +79,15 @@ void mk_T_maps(ParamGetHI *par)
   print_info(">    Relative time ellapsed %.1lf ms\n\n", ms[GH_T_MAPS] + ms[GH_T_REDUCE] + ms[GH_T_D2H]);
 }
 
+/* The same stage without waiting: accumulation, reduction, scaling and the download are queued; write_maps
+ * starts on shell s as soon as it has landed (gh_cuda_wait_shells) and prints the stage's timing at its end. */
+void mk_T_maps_begin(ParamGetHI *par)
+{
+  print_info("*** Making maps\n Collecting masses\n Normalizing to temperature\n");
+  check(gh_cuda_mk_T_maps_begin(par->cuda, par->maps_HI), "mk_T_maps");
+  par->maps_streaming = 1;
+}
+
 void end_fftw(ParamGetHI *par)
 {
   if (!par || !par->cuda) return;

@@ -236,7 +236,10 @@ static void write_nu_table(const ParamGetHI *par)
 
 /* Every rank writes the shells it owns (the reference gathers everything on rank 0 first and writes the files
  * one after the other, with a float copy per map, src/io_gh.c:69-131).  One file per shell, so the shells are
- * written concurrently: the byte-swap runs on several cores and the file system sees several streams. */
+ * written concurrently: the byte-swap runs on several cores and the file system sees several streams.
+ * After mk_T_maps_begin the writers also overlap the device->host copy: shell s is written as soon as the
+ * chunk holding it has landed, while later shells are still on the wire (and, on several GPUs, while other
+ * ranks are still reducing). */
 void write_maps(ParamGetHI *par)
 {
   if (par->rank == 0) write_nu_table(par); /* the shipped Makefile's -D_DEBUG output, src/io_gh.c:112-114 */
@@ -247,9 +250,18 @@ void write_maps(ParamGetHI *par)
   for (int s = 0; s < par->n_shells_here; s++) {
     char fn[300];
     snprintf(fn, sizeof(fn), "%s_%03d.fits", par->prefixOut, par->shell0_here + s + 1);
+    if (par->maps_streaming && gh_cuda_wait_shells(par->cuda, s + 1)) { n_fail++; continue; }
     const int rc = gh_write_healpix_map(par->maps_HI + (size_t)s * npix, par->n_side, fn);
     if (rc == 1) n_exist++;
     else if (rc) n_fail++;
+  }
+  if (par->maps_streaming) {
+    if (gh_cuda_wait(par->cuda, NULL)) report_error(1, "mk_T_maps: %s\n", gh_cuda_last_error());
+    double ms[GH_T_NSLOTS];
+    if (!gh_cuda_stage_times(par->cuda, ms))
+      print_info(">    Relative time ellapsed %.1lf ms (maps; the download and the writers overlapped it)\n\n",
+                 ms[GH_T_MAPS] + ms[GH_T_REDUCE] + ms[GH_T_D2H]);
+    par->maps_streaming = 0;
   }
   if (n_exist) report_error(0, "%d of the %s_###.fits files exist and were left untouched\n", n_exist, par->prefixOut);
   if (n_fail) report_error(1, "could not write %d of the %s_###.fits files\n", n_fail, par->prefixOut);

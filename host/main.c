@@ -23,8 +23,8 @@ static int run_rank(const char *fname, int rank, int nranks, int device, const v
   print_info("Seed : %u\n", par->seed_rng);
   create_d_and_vr_fields(par);
   get_HI(par);
-  mk_T_maps(par);
-  write_maps(par); /* every rank writes the shells it owns */
+  mk_T_maps_begin(par); /* non-blocking mk_T_maps ... */
+  write_maps(par);      /* ... every rank writes the shells it owns as they arrive from the device */
   if (NodeThis == 0) timer(5);
   print_info("\n");
   print_info("|-------------------------------------------------|\n\n");

@@ -136,6 +136,15 @@ int gh_cuda_get_HI(gh_cuda_ctx *ctx);
  * par->maps_HI.  maps_host should be page-locked for full PCIe speed (gh_cuda_host_alloc). */
 int gh_cuda_mk_T_maps(gh_cuda_ctx *ctx, float *maps_host);
 
+/* Streaming form of mk_T_maps for an overlapped writer (the reference writes the files only after
+ * everything has been gathered on rank 0, src/io_gh.c:109-131): _begin enqueues accumulation, reduction,
+ * scaling and the download of this rank's shells in chunks of whole shells and returns at once;
+ * gh_cuda_wait_shells(ctx, n) returns once this rank's first n shells (n < 0: all) of the most recently begun
+ * download are complete in maps_host.  maps_host should come from gh_cuda_host_alloc.  Thread-safe for
+ * several waiting threads. */
+int gh_cuda_mk_T_maps_begin(gh_cuda_ctx *ctx, float *maps_host);
+int gh_cuda_wait_shells(gh_cuda_ctx *ctx, int n_shells);
+
 /* whole hot path, main_gh.c:52-62: the three calls above back to back */
 int gh_cuda_run(gh_cuda_ctx *ctx, double *sigma2_gauss_out, float *maps_host);
 

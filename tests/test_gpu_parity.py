@@ -411,3 +411,29 @@ def test_fft_256_against_oracle(oracle, tables_nu64):
     ref_v = oracle.c2r_3d(vk)[:, :, :n] * norm
     assert field_err(dens, ref_d) < TOL
     assert field_err(vpot, ref_v) < TOL
+
+
+def test_streamed_map_download_shell_by_shell(tables_nu64):
+    """gh_cuda_mk_T_maps_begin / gh_cuda_wait_shells: shells become readable in order while later ones are still
+    being copied; the result equals the blocking mk_T_maps.  nside 512 makes a shell 12 MiB, so the 64 shells
+    leave in chunks of 3."""
+    from crime_b200 import GetHI, params_from_tables
+    p = params_from_tables(tables_nu64, n_grid=64, n_side=512, seed=9)
+    with GetHI(p) as g:
+        g.create_d_and_vr_fields()
+        g.get_HI()
+        ref = g.mk_T_maps().copy()
+        ref_sum = ref.sum(axis=1, dtype=np.float64)
+        assert (ref_sum > 0).any()
+        g.maps_HI[:] = -1.0
+        buf = g.mk_T_maps_begin()
+        for s in range(g.n_shells_here):
+            g.wait_shells(s + 1)
+            got = buf[s]
+            assert got.min() >= 0.0                                   # landed (the buffer was filled with -1)
+            nz = ref[s] != 0
+            assert np.array_equal(got != 0, nz)
+            if nz.any():
+                assert np.abs(got[nz] / ref[s][nz] - 1).max() < 1e-5
+        g.wait_shells(-1)
+        g.wait()
