@@ -163,9 +163,21 @@ def cpu_reference_run(n_grid: int, n_side: int, n_nu: int, steps: int, warmup: i
     """Time the reference's own create_d_and_vr_fields + get_HI + mk_T_maps (oracle/_ref, all host
     threads); falls back to the oracle port when the prebuilt reference is absent."""
     from oracle.binding import Oracle, Reference, write_nutable, write_param_file
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    cores = int(os.environ["OMP_NUM_THREADS"])
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    # torchrun exports OMP_NUM_THREADS=1 to every rank unless the user set it; the CPU arm runs on rank 0 alone and
+    # is meant to use every host thread it can, so that default is overridden (an explicit GH_CPU_THREADS wins)
+    cores = int(os.environ.get("GH_CPU_THREADS", "0")) or avail
+    if "LOCAL_RANK" not in os.environ and os.environ.get("OMP_NUM_THREADS"):
+        cores = int(os.environ["OMP_NUM_THREADS"])
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    try:  # libgomp may already be initialised in this process: set the thread count through its API as well
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)
+    except OSError:
+        pass
     cells = float(n_grid) ** 3
     times = []
     if Reference.available():
