@@ -102,7 +102,7 @@ def params_to_dict(p: GhCudaParams) -> dict:
 
 def load_library(path: os.PathLike | None = None) -> C.CDLL:
     """Load libgh_cuda.so and declare every entry point of include/gh_cuda.h.  Raises if absent."""
-    path = Path(path) if path else LIB_PATH
+    path = Path(path) if path else Path(os.environ.get("GH_CUDA_LIB", LIB_PATH))  # GH_CUDA_LIB: A/B-testing a build
     if not path.exists():
         raise RuntimeError(
             f"{path} not found: the CUDA extension has not been built "
