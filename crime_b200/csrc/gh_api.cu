@@ -453,6 +453,8 @@ extern "C" int gh_cuda_create(const gh_cuda_params *p, int rank, int nranks, con
   } while (0)
 
   CREATE_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  // one rank only for now: the fused pass has not been through the multi-GPU parity run yet
+  c->fuse_vel = nranks == 1 && getenv("GH_NO_FUSE_VEL") == nullptr;
   CREATE_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   CREATE_OK(cudaStreamCreateWithFlags(&c->pull_stream, cudaStreamNonBlocking));
   CREATE_OK(cudaEventCreateWithFlags(&c->ev_bar, cudaEventDisableTiming));
@@ -846,9 +848,21 @@ extern "C" int gh_cuda_run_async(gh_cuda_ctx *c, float *maps_host)
   GH_CTX(c);
   if (!c->k_injected && gh_cuda_generate_k(c)) return 1;
   if (gh_cuda_fft_fields(c)) return 1;
-  if (gh_cuda_radial_velocity(c)) return 1;
-  if (enqueue_sigma(c)) return 1;
-  if (gh_cuda_get_HI(c)) return 1;
+  if (c->fuse_vel) {
+    // nobody reads the radial velocity between the stages here: one pass does velocity + get_HI
+    if (enqueue_sigma(c)) return 1;
+    {
+      StageTimer t(c, GH_T_VEL);  // what is left of the stage: the two-plane halo exchange
+      if (gh_launch_halo_exchange(c)) return 1;
+    }
+    c->fft_stats_blocks = 0;
+    StageTimer t(c, GH_T_GETHI);
+    if (gh_launch_velocity_get_HI(c)) return 1;
+  } else {
+    if (gh_cuda_radial_velocity(c)) return 1;
+    if (enqueue_sigma(c)) return 1;
+    if (gh_cuda_get_HI(c)) return 1;
+  }
   return enqueue_maps(c, maps_host);
 }
 

@@ -161,9 +161,65 @@ __global__ void __launch_bounds__(256) get_HI_kernel(GhDev d, Axes3 axes, float 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// radial velocity + get_HI in one pass (used by gh_cuda_run / gh_cuda_run_async, where nobody looks at the
+// radial velocity itself): the velocity never goes to memory, so the pair costs 8 B read (phi, delta) + 8 B
+// written (HI mass, Delta z_RSD) per cell instead of 24.  Same thread mapping and the very same expressions as
+// the two kernels above, so the results are bit-identical to running them one after the other
+// (tests/test_gpu_parity.py).
+__global__ void __launch_bounds__(256) velocity_get_HI_kernel(GhDev d, Axes3 axes, const float *__restrict__ vpot,
+                                                              const float *__restrict__ plane_lo,
+                                                              const float *__restrict__ plane_hi, float *__restrict__ dens,
+                                                              float *__restrict__ dz_out, const double *__restrict__ sigma_stats)
+{
+  const GetHIConsts k = make_gethi_consts(d, (float)sigma_stats[5]);
+  const int ngx = 2 * d.nh;
+  const int iy = blockIdx.y, iz = blockIdx.z;
+  const float hidx = d.half_inv_dx;
+  const AxisF ax = axes.x;
+  const float y = axes.y.at(iy), z = axes.z.at(iz);
+  const int iy_hi = (iy == d.n - 1) ? 0 : iy + 1, iy_lo = (iy == 0) ? d.n - 1 : iy - 1;
+  const size_t plane = (size_t)ngx * d.n;
+  const float *p0 = vpot + (size_t)iz * plane;
+  const float *pz_lo = ((iz == 0) ? plane_lo : p0 - plane) + (size_t)iy * ngx;
+  const float *pz_hi = ((iz == d.nz_here - 1) ? plane_hi : p0 + plane) + (size_t)iy * ngx;
+  const float *row = p0 + (size_t)iy * ngx, *row_hi = p0 + (size_t)iy_hi * ngx, *row_lo = p0 + (size_t)iy_lo * ngx;
+  const size_t base_off = (size_t)iz * plane + (size_t)iy * ngx;
+  const int lane = threadIdx.x & 31;
+  const float yz2 = fmaf(y, y, z * z);
+  const float yz2_h = fmaf(y, y, __fmul_rn(z, z));  // get_HI_kernel's spelling of the same sum
+  const int nper = d.n / 2;
+  for (int base = blockIdx.x * blockDim.x; base < nper; base += gridDim.x * blockDim.x) {
+    const int ip = base + threadIdx.x;
+    const bool act = ip < nper;
+    const int ix = act ? 2 * ip : 0;
+    const float2 c = __ldg(reinterpret_cast<const float2 *>(row + ix));
+    const float2 yh = __ldg(reinterpret_cast<const float2 *>(row_hi + ix)), yl = __ldg(reinterpret_cast<const float2 *>(row_lo + ix));
+    const float2 zh = __ldg(reinterpret_cast<const float2 *>(pz_hi + ix)), zl = __ldg(reinterpret_cast<const float2 *>(pz_lo + ix));
+    const float2 dv = *reinterpret_cast<const float2 *>(dens + base_off + ix);
+    float left = __shfl_up_sync(0xffffffffu, c.y, 1), right = __shfl_down_sync(0xffffffffu, c.x, 1);
+    if (lane == 0) left = __ldg(row + ((ix == 0) ? d.n - 1 : ix - 1));
+    if (lane == 31 || ip >= nper - 1) right = __ldg(row + ((ix + 2 >= d.n) ? 0 : ix + 2));
+    if (!act) continue;
+    const float x0 = ax.at(ix), x1 = ax.at(ix + 1);
+    const float vx0 = hidx * (c.y - left), vx1 = hidx * (right - c.x);
+    const float vy0 = hidx * (yh.x - yl.x), vy1 = hidx * (yh.y - yl.y);
+    const float vz0 = hidx * (zh.x - zl.x), vz1 = hidx * (zh.y - zl.y);
+    const float ir0 = rsqrtf(fmaf(x0, x0, yz2)), ir1 = rsqrtf(fmaf(x1, x1, yz2));
+    const float rv0 = fmaf(vx0, x0, fmaf(vy0, y, vz0 * z)) * ir0;
+    const float rv1 = fmaf(vx1, x1, fmaf(vy1, y, vz1 * z)) * ir1;
+    float2 m, dzr;
+    gh_gethi_cell(k, fmaf(x0, x0, yz2_h), dv.x, rv0, m.x, dzr.x);
+    gh_gethi_cell(k, fmaf(x1, x1, yz2_h), dv.y, rv1, m.y, dzr.y);
+    *reinterpret_cast<float2 *>(dens + base_off + ix) = m;
+    *reinterpret_cast<float2 *>(dz_out + base_off + ix) = dzr;
+  }
+}
+
 }  // namespace
 
-int gh_launch_radial_velocity(gh_cuda_ctx *c)
+// neighbour planes of the velocity potential for this slab's first and last plane
+static int halo_planes(gh_cuda_ctx *c, const float **lo_out, const float **hi_out)
 {
   const GhDev &d = c->d;
   const float *vpot = reinterpret_cast<const float *>(c->gridB);
@@ -184,6 +240,39 @@ int gh_launch_radial_velocity(gh_cuda_ctx *c)
     lo = vpot + (size_t)(d.n - 1) * plane;  // src/fourier.c:425-427
     hi = vpot;
   }
+  *lo_out = lo;
+  *hi_out = hi;
+  return 0;
+}
+
+int gh_launch_halo_exchange(gh_cuda_ctx *c)
+{
+  const float *lo, *hi;
+  return halo_planes(c, &lo, &hi);
+}
+
+// call after gh_launch_halo_exchange on several ranks (the exchange is not repeated here)
+int gh_launch_velocity_get_HI(gh_cuda_ctx *c)
+{
+  const GhDev &d = c->d;
+  const float *vpot = reinterpret_cast<const float *>(c->gridB);
+  const size_t plane = (size_t)2 * d.nh * d.n;
+  const float *lo = (d.nranks > 1) ? c->halo_lo : vpot + (size_t)(d.n - 1) * plane;
+  const float *hi = (d.nranks > 1) ? c->halo_hi : vpot;
+  dim3 grid((d.n / 2 + 255) / 256, d.n, d.nz_here);
+  const Axes3 axes = {make_axis(d.dx, d.pos_obs[0], 0), make_axis(d.dx, d.pos_obs[1], 0), make_axis(d.dx, d.pos_obs[2], d.iz0)};
+  velocity_get_HI_kernel<<<grid, 256, 0, c->stream>>>(d, axes, vpot, lo, hi, reinterpret_cast<float *>(c->gridA),
+                                                      reinterpret_cast<float *>(c->gridC), c->d_partials);
+  GH_LAUNCH_CHECK(c);
+  return 0;
+}
+
+int gh_launch_radial_velocity(gh_cuda_ctx *c)
+{
+  const GhDev &d = c->d;
+  const float *vpot = reinterpret_cast<const float *>(c->gridB);
+  const float *lo, *hi;
+  if (halo_planes(c, &lo, &hi)) return 1;
   dim3 grid((d.n / 2 + 255) / 256, d.n, d.nz_here);
   const Axes3 axes = {make_axis(d.dx, d.pos_obs[0], 0), make_axis(d.dx, d.pos_obs[1], 0), make_axis(d.dx, d.pos_obs[2], d.iz0)};
   radial_velocity_kernel<<<grid, 256, 0, c->stream>>>(d, axes, vpot, lo, hi, reinterpret_cast<float *>(c->gridC));

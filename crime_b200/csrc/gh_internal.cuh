@@ -71,6 +71,7 @@ struct gh_cuda_ctx {
   ncclComm_t comm;
   bool have_comm;
   bool have_peers;                 // peer mappings established (nranks>1, same node)
+  bool fuse_vel;                   // gh_cuda_run*: radial velocity and get_HI in one pass
   bool rebalance;                  // accumulate equal-cost plane ranges, pulling foreign planes from peers
   int map_bounds[GH_MAX_RANKS + 1];
   cudaStream_t pull_stream;
@@ -137,6 +138,8 @@ int gh_launch_radial_velocity(gh_cuda_ctx *c);
 int gh_launch_sigma(gh_cuda_ctx *c);  // leaves (sum, sumsq) in c->d_partials[0..1]
 int gh_launch_sigma_finish(gh_cuda_ctx *c);  // d_partials[4] = mean, [5] = sigma2_gauss
 int gh_launch_get_HI(gh_cuda_ctx *c);
+int gh_launch_halo_exchange(gh_cuda_ctx *c);
+int gh_launch_velocity_get_HI(gh_cuda_ctx *c);
 int gh_launch_accumulate(gh_cuda_ctx *c, const float *mass, const float *dzrsd, int iz_base, int zg_base, int nplanes);
 int gh_stream_barrier(gh_cuda_ctx *c);  // every rank has reached this point of its stream
 int gh_launch_accumulate_audit(gh_cuda_ctx *c, float eps_scale, unsigned long long *d_counts);

@@ -437,3 +437,24 @@ def test_streamed_map_download_shell_by_shell(tables_nu64):
                 assert np.abs(got[nz] / ref[s][nz] - 1).max() < 1e-5
         g.wait_shells(-1)
         g.wait()
+
+
+def test_fused_velocity_get_HI_equals_the_two_stages(tables_nu64):
+    """gh_cuda_run fuses radial velocity and get_HI into one pass (the velocity never goes to memory); HI mass and
+    Delta z_RSD must be bit-identical to running the two stages one after the other, and so must sigma2."""
+    from crime_b200 import GetHI, params_from_tables
+    from crime_b200.abi import GRID_DENS, GRID_RVEL
+    n = 128
+    p = params_from_tables(tables_nu64, n_grid=n, n_side=32, seed=77)
+    with GetHI(p) as g:
+        s2 = g.create_d_and_vr_fields()
+        g.get_HI()
+        mass, dz = g.download_grid(GRID_DENS).copy(), g.download_grid(GRID_RVEL).copy()
+        maps = g.mk_T_maps().copy()
+        fused = g.run().copy()
+        assert g.sigma2_gauss == s2
+        assert np.array_equal(g.download_grid(GRID_DENS)[:, :, :n], mass[:, :, :n])
+        assert np.array_equal(g.download_grid(GRID_RVEL)[:, :, :n], dz[:, :, :n])
+        assert np.array_equal(fused != 0, maps != 0)
+        nz = maps != 0
+        assert np.abs(fused[nz] / maps[nz] - 1).max() < 1e-5
