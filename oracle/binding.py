@@ -15,6 +15,7 @@ from crime_b200.abi import GhCudaParams, N_SUBPART, params_from_dict
 HERE = Path(__file__).resolve().parent
 ORACLE_SO = HERE / "liboracle.so"
 REF_SO = HERE / "_ref" / "libgethi_ref.so"
+REF_SO_REGULAR = HERE / "_ref" / "libgethi_ref_regular.so"  # built without -D_IRREGULAR_NUTABLE
 REF_EXE = HERE / "_ref" / "GetHI"
 REFERENCE_ROOT = Path(os.environ.get("CRIME_REFERENCE", "/root/reference"))
 
@@ -212,13 +213,16 @@ class Reference:
               "growth_v_arr", "nu0_arr", "nuf_arr")
 
     @staticmethod
-    def available() -> bool:
-        return REF_SO.exists()
+    def available(regular: bool = False) -> bool:
+        return (REF_SO_REGULAR if regular else REF_SO).exists()
 
-    def __init__(self):
-        if not REF_SO.exists():
-            raise RuntimeError(f"{REF_SO} missing (needs the reference tree to build; see oracle/Makefile)")
-        self.lib = lib = C.CDLL(str(REF_SO))
+    def __init__(self, regular: bool = False):
+        """regular=True: the build without -D_IRREGULAR_NUTABLE (param keys nu_min / nu_max / n_nu)."""
+        so = REF_SO_REGULAR if regular else REF_SO
+        self.regular = regular
+        if not so.exists():
+            raise RuntimeError(f"{so} missing (needs the reference tree to build; see oracle/Makefile)")
+        self.lib = lib = C.CDLL(str(so))
         lib.ref_read_run_params.argtypes = [C.c_char_p]
         lib.ref_read_run_params.restype = _vp
         for n in ("ref_create_d_and_vr_fields", "ref_get_HI", "ref_mk_T_maps", "ref_write_maps", "ref_free"):
@@ -261,9 +265,11 @@ class Reference:
             seed_rng=int(g("seed_rng")), do_smoothing=int(g("do_smoothing")), r2_smooth=g("r2_smooth"),
             fgrowth_0=g("fgrowth_0"), hubble_0=g("hubble_0"), numk=int(g("numk")), logkmin=g("logkmin"),
             logkmax=g("logkmax"), idlogk=g("idlogk"), n_scal=g("n_scal"), nz_tab=5001, glob_idr=g("glob_idr"),
-            dz_tab=0.001, n_side=int(g("n_side")), n_nu=int(g("n_nu")), irregular_nutable=1, nu_min=g("nu_min"),
-            nu_max=g("nu_max"), OmegaB=g("OmegaB"), hhub=g("hhub"))
+            dz_tab=0.001, n_side=int(g("n_side")), n_nu=int(g("n_nu")), irregular_nutable=0 if self.regular else 1,
+            nu_min=g("nu_min"), nu_max=g("nu_max"), OmegaB=g("OmegaB"), hhub=g("hhub"))
         for t in self.TABLES:
+            if self.regular and t in ("nu0_arr", "nuf_arr"):
+                continue
             d[t] = self.table(par, t)
         return d
 
@@ -271,13 +277,16 @@ class Reference:
         return params_from_dict(self.params_dict(par))
 
 
-def write_param_file(path, *, n_grid, n_side, nutable, pk_file, prefix, seed=1001, r_smooth=2.0, omega_M=0.3,
-                     omega_L=0.7, omega_B=0.049, h=0.67, w=-1.0, ns=0.96, sigma_8=0.8, do_psources=0):
-    """A GetHI param file with the reference's keys (param_GetHI_sample.ini)."""
+def write_param_file(path, *, n_grid, n_side, pk_file, prefix, nutable=None, regular=None, seed=1001, r_smooth=2.0,
+                     omega_M=0.3, omega_L=0.7, omega_B=0.049, h=0.67, w=-1.0, ns=0.96, sigma_8=0.8, do_psources=0):
+    """A GetHI param file with the reference's keys (param_GetHI_sample.ini).  nutable: file of shell edges (the
+    -D_IRREGULAR_NUTABLE personality); regular=(nu_min, nu_max, n_nu): the other one (src/io_gh.c:234-241)."""
+    freq = (f"frequencies_filename= {nutable}\n" if regular is None else
+            f"nu_min= {regular[0]}\nnu_max= {regular[1]}\nn_nu= {regular[2]}\n")
     Path(path).write_text(
         f"prefix_out= {prefix}\npk_filename= {pk_file}\nomega_M= {omega_M}\nomega_L= {omega_L}\n"
         f"omega_B= {omega_B}\nh= {h}\nw= {w}\nns= {ns}\nsigma_8= {sigma_8}\nr_smooth= {r_smooth}\n"
-        f"frequencies_filename= {nutable}\nn_side= {n_side}\nn_grid= {n_grid}\nseed= {seed}\n"
+        f"{freq}n_side= {n_side}\nn_grid= {n_grid}\nseed= {seed}\n"
         f"do_psources= {do_psources}\n")
 
 

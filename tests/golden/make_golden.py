@@ -80,15 +80,52 @@ def run_case(ref, tmp, name, n_grid, n_side, n_nu, seed, full):
     print(name, "written", (HERE / f"{name}.npz").stat().st_size // 1024, "KiB")
 
 
+def run_regular_case(tmp, name, n_grid, n_side, n_nu, seed, nu_min=355.0, nu_max=945.0):
+    """The reference's other compile-time personality (no -D_IRREGULAR_NUTABLE, src/pixelize.c:176-178,216):
+    uniform shells from nu_min / nu_max / n_nu and a C truncation that also puts (nu_min - dnu, nu_min) into
+    shell 0.  Stores the map stage's inputs and output."""
+    ref = Reference(regular=True)
+    ini = f"{tmp}/{name}.ini"
+    write_param_file(ini, n_grid=n_grid, n_side=n_side, regular=(nu_min, nu_max, n_nu),
+                     pk_file=str(ROOT / "data" / "Pk_synth.dat"), prefix=f"{tmp}/{name}", seed=seed)
+    par = ref.read_run_params(ini)
+    d = ref.params_dict(par)
+    assert d["irregular_nutable"] == 0
+    out = {k: np.asarray(d[k]) for k in SCALARS}
+    out["pos_obs"] = np.asarray(d["pos_obs"])
+    for t in Reference.TABLES:
+        if t in d:
+            out[t] = d[t]
+    out["omp_threads"] = np.asarray(int(os.environ["OMP_NUM_THREADS"]))
+    n, nh = n_grid, n_grid // 2 + 1
+    rs = (n, n, 2 * nh)
+    ref.lib.ref_create_d_and_vr_fields(par)
+    out["sigma2_gauss"] = np.asarray(ref.get(par, "sigma2_gauss"))
+    ref.lib.ref_get_HI(par)
+    out["mass"] = ref.grid(par, "dens", rs).copy()
+    out["dz_rsd"] = ref.grid(par, "rvel", rs).copy()
+    ref.lib.ref_mk_T_maps(par)
+    out["maps"] = ref.grid(par, "maps_HI", (n_nu, 12 * n_side * n_side)).copy()
+    for k in ("mass", "dz_rsd"):
+        out[k][:, :, n:] = 0
+    np.savez_compressed(HERE / f"{name}.npz", **out)
+    print(name, "written", (HERE / f"{name}.npz").stat().st_size // 1024, "KiB")
+
+
 def main():
+    """no argument: every fixture; `regular`: only ref_n32_regular.npz (leaves the others untouched)."""
     if "OMP_NUM_THREADS" not in os.environ:
         raise SystemExit("set OMP_NUM_THREADS (the realisation depends on it)")
-    ref = Reference()
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
     with tempfile.TemporaryDirectory() as tmp:
-        run_case(ref, tmp, "ref_n32", n_grid=32, n_side=16, n_nu=16, seed=1001, full=True)
-        # tables only (they do not depend on n_grid except through l_box / pos_obs, src/cosmo.c:361-364)
-        run_case(ref, tmp, "ref_tables_nu64", n_grid=512, n_side=256, n_nu=64, seed=1001, full=False)
-        run_case(ref, tmp, "ref_tables_nu150", n_grid=1024, n_side=512, n_nu=150, seed=1001, full=False)
+        if only in ("", "irregular"):
+            ref = Reference()
+            run_case(ref, tmp, "ref_n32", n_grid=32, n_side=16, n_nu=16, seed=1001, full=True)
+            # tables only (they do not depend on n_grid except through l_box / pos_obs, src/cosmo.c:361-364)
+            run_case(ref, tmp, "ref_tables_nu64", n_grid=512, n_side=256, n_nu=64, seed=1001, full=False)
+            run_case(ref, tmp, "ref_tables_nu150", n_grid=1024, n_side=512, n_nu=150, seed=1001, full=False)
+        if only in ("", "regular"):
+            run_regular_case(tmp, "ref_n32_regular", n_grid=32, n_side=16, n_nu=20, seed=1001)
 
 
 if __name__ == "__main__":

@@ -92,6 +92,24 @@ def test_maps_from_reference_grids(gh32, golden_n32):
     assert np.abs(maps[nz] / ref[nz] - 1).max() < TOL
 
 
+def test_maps_from_reference_grids_regular_table_build():
+    """mk_T_maps with irregular_nutable=0 against the reference compiled without -D_IRREGULAR_NUTABLE
+    (tests/golden/ref_n32_regular.npz): uniform shells, C truncation below nu_min, regular prefactors."""
+    from conftest import GOLDEN
+    from crime_b200 import GetHI
+    from crime_b200.abi import GRID_DENS, GRID_RVEL
+    g = dict(np.load(GOLDEN / "ref_n32_regular.npz"))
+    with GetHI(params_of(g)) as gh:
+        gh.upload_grid(GRID_DENS, g["mass"])
+        gh.upload_grid(GRID_RVEL, g["dz_rsd"])
+        maps = gh.mk_T_maps().copy()
+    ref = g["maps"]
+    assert maps.shape == ref.shape
+    assert np.array_equal(maps != 0, ref != 0)
+    nz = ref != 0
+    assert np.abs(maps[nz] / ref[nz] - 1).max() < TOL
+
+
 def test_sub_particle_offsets_match_oracle(gh32, oracle, golden_n32):
     assert np.array_equal(gh32.subparticle_offsets(), oracle.subparticle_offsets(params_of(golden_n32)))
 

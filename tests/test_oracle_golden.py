@@ -120,6 +120,22 @@ def test_maps_match_reference(oracle, golden_n32):
     assert np.abs(maps[nz] / ref[nz] - 1).max() < 2e-6
 
 
+def test_regular_table_personality_matches_its_reference_build(oracle):
+    """The reference compiled WITHOUT -D_IRREGULAR_NUTABLE (oracle/_ref/libgethi_ref_regular.so): uniform shells
+    from nu_min / nu_max / n_nu, `(int)(inv_dnu*(nu-nu_min))` with its truncation quirk (src/pixelize.c:176-178,216)
+    and the regular prefactors (src/pixelize.c:251-253).  Same inputs, same hit pixels, same values."""
+    from conftest import GOLDEN
+    g = dict(np.load(GOLDEN / "ref_n32_regular.npz"))
+    assert int(g["irregular_nutable"]) == 0
+    p = params_of(g)
+    maps = oracle.normalize_maps(p, oracle.accumulate_maps(p, g["mass"], g["dz_rsd"]))
+    ref = g["maps"]
+    assert ref.shape == (20, 12 * 16 * 16) and (ref[0] != 0).any() and (ref[-1] != 0).any()
+    assert np.array_equal(maps != 0, ref != 0)
+    nz = ref != 0
+    assert np.abs(maps[nz] / ref[nz] - 1).max() < 2e-6
+
+
 def test_subparticle_offsets_are_the_first_30_draws(oracle, golden_n32):
     p = params_of(golden_n32)
     off = oracle.subparticle_offsets(p)
