@@ -355,6 +355,52 @@ static int setup_peers(gh_cuda_ctx *c)
   return 0;
 }
 
+// Opt-in (GH_SPARSE_REDUCE=1): map every peer's accumulation stack too, for the sparse map reduction
+// (gh_pixelize.cu).  Same handle exchange as setup_peers; a failure anywhere turns the feature off everywhere.
+static int setup_map_peers(gh_cuda_ctx *c)
+{
+  const int P = c->d.nranks, me = c->d.rank;
+  const size_t hsz = sizeof(cudaIpcMemHandle_t);
+  cudaIpcMemHandle_t mine;
+  GH_CUDA_OK(cudaIpcGetMemHandle(&mine, c->maps));
+  char *d_all = nullptr;
+  GH_CUDA_OK(cudaMalloc(&d_all, hsz * P));
+  GH_CUDA_OK(cudaMemcpyAsync(d_all + hsz * me, &mine, hsz, cudaMemcpyHostToDevice, c->stream));
+  GH_NCCL_OK(ncclAllGather(d_all + hsz * me, d_all, hsz, ncclChar, c->comm, c->stream));
+  cudaIpcMemHandle_t *all = (cudaIpcMemHandle_t *)malloc(hsz * P);
+  GH_REQUIRE(all, "out of host memory");
+  cudaError_t e = cudaMemcpyAsync(all, d_all, hsz * P, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d_all);
+  if (e != cudaSuccess) { free(all); gh_set_error("IPC handle exchange failed: %s", cudaGetErrorString(e)); return 1; }
+  bool ok = true;
+  for (int q = 0; q < P && ok; ++q) {
+    if (q == me) { c->map_peers[q] = c->maps; continue; }
+    void *pm = nullptr;
+    if (cudaIpcOpenMemHandle(&pm, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = false;
+    else c->map_peers[q] = (float *)pm;
+  }
+  free(all);
+  cudaGetLastError();
+  int flag = ok ? 1 : 0;
+  GH_CUDA_OK(cudaMemcpyAsync(c->d_barrier, &flag, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  GH_NCCL_OK(ncclAllReduce(c->d_barrier, c->d_barrier, 1, ncclInt, ncclMin, c->comm, c->stream));
+  GH_CUDA_OK(cudaMemcpyAsync(&flag, c->d_barrier, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  GH_CUDA_OK(cudaStreamSynchronize(c->stream));
+  GH_CUDA_OK(cudaMemsetAsync(c->d_barrier, 0, sizeof(int), c->stream));
+  if (flag != 1) {
+    for (int q = 0; q < P; ++q) {
+      if (q != me && c->map_peers[q]) cudaIpcCloseMemHandle(c->map_peers[q]);
+      c->map_peers[q] = nullptr;
+    }
+    cudaGetLastError();
+    return 0;
+  }
+  GH_CUDA_OK(cudaMalloc(&c->d_ext, sizeof(int) * 2 * (size_t)c->d.n_nu_pad * (P + 1)));
+  c->sparse_reduce = true;
+  return 0;
+}
+
 extern "C" int gh_cuda_destroy(gh_cuda_ctx *c)
 {
   if (!c) return 0;
@@ -370,6 +416,9 @@ extern "C" int gh_cuda_destroy(gh_cuda_ctx *c)
     if (c->peers.A[q]) cudaIpcCloseMemHandle(c->peers.A[q]);
     if (c->peers.C[q]) cudaIpcCloseMemHandle(c->peers.C[q]);
   }
+  for (int q = 0; q < c->d.nranks && q < GH_MAX_RANKS; ++q)
+    if (q != c->d.rank && c->map_peers[q]) cudaIpcCloseMemHandle(c->map_peers[q]);
+  cudaFree(c->d_ext);
   cudaFree(c->d_barrier);
   if (c->have_comm) ncclCommDestroy(c->comm);
   cudaFree(c->gridA); cudaFree(c->gridB); cudaFree(c->gridC);
@@ -526,6 +575,7 @@ extern "C" int gh_cuda_create(const gh_cuda_params *p, int rank, int nranks, con
     }
     c->have_comm = true;
     if (setup_peers(c)) { gh_cuda_destroy(c); return 1; }
+    if (c->have_peers && getenv("GH_SPARSE_REDUCE") && setup_map_peers(c)) { gh_cuda_destroy(c); return 1; }
   }
   CREATE_OK(cudaStreamSynchronize(c->stream));
 #undef CREATE_OK
@@ -767,9 +817,22 @@ static int enqueue_maps(gh_cuda_ctx *c, float *maps_host)
       // up with the sum of its own shells, then scales just those
       StageTimer t(c, GH_T_REDUCE);
       const size_t per = (size_t)(d.n_nu_pad / d.nranks) * d.npix;
-      if (c->copy_pending[cur]) GH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_copied[cur], 0));
-      GH_NCCL_OK(ncclReduceScatter(c->maps, c->maps_recv, per, ncclFloat, ncclSum, c->comm, c->stream));
-      if (gh_launch_scale_maps(c, c->maps_recv, s0, n_here)) return 1;
+      if (c->sparse_reduce) {
+        // own intervals -> all-gather (doubles as "everybody has finished accumulating") -> pull, sum, scale
+        int *own = c->d_ext, *all = c->d_ext + 2 * (size_t)d.n_nu_pad;
+        GH_CUDA_OK(cudaMemsetAsync(own, 0x7f, sizeof(int) * d.n_nu_pad, c->stream));               // lo = huge
+        GH_CUDA_OK(cudaMemsetAsync(own + d.n_nu_pad, 0, sizeof(int) * d.n_nu_pad, c->stream));     // hi = 0: empty
+        if (gh_launch_shell_extents(c, own, own + d.n_nu_pad)) return 1;
+        GH_NCCL_OK(ncclAllGather(own, all, 2 * (size_t)d.n_nu_pad, ncclInt, c->comm, c->stream));
+        if (c->copy_pending[cur]) GH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_copied[cur], 0));
+        if (gh_launch_sparse_reduce(c, all, c->maps_recv, s0, n_here)) return 1;
+        // nobody may zero its stack (next realisation) while a peer is still reading it
+        if (gh_stream_barrier(c)) return 1;
+      } else {
+        if (c->copy_pending[cur]) GH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_copied[cur], 0));
+        GH_NCCL_OK(ncclReduceScatter(c->maps, c->maps_recv, per, ncclFloat, ncclSum, c->comm, c->stream));
+        if (gh_launch_scale_maps(c, c->maps_recv, s0, n_here)) return 1;
+      }
     }
   }
   float *result = c->out_buf[cur];

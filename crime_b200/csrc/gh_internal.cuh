@@ -72,6 +72,9 @@ struct gh_cuda_ctx {
   bool have_comm;
   bool have_peers;                 // peer mappings established (nranks>1, same node)
   bool fuse_vel;                   // gh_cuda_run*: radial velocity and get_HI in one pass
+  bool sparse_reduce;              // opt-in: map reduction by pulling the peers' touched pixel intervals (GH_SPARSE_REDUCE=1)
+  float *map_peers[GH_MAX_RANKS];  // every rank's accumulation stack (peer-mapped), sparse_reduce only
+  int *d_ext;                      // [2][n_nu_pad] own intervals, then [nranks][2][n_nu_pad] gathered
   bool rebalance;                  // accumulate equal-cost plane ranges, pulling foreign planes from peers
   int map_bounds[GH_MAX_RANKS + 1];
   cudaStream_t pull_stream;
@@ -144,6 +147,8 @@ int gh_launch_accumulate(gh_cuda_ctx *c, const float *mass, const float *dzrsd, 
 int gh_stream_barrier(gh_cuda_ctx *c);  // every rank has reached this point of its stream
 int gh_launch_accumulate_audit(gh_cuda_ctx *c, float eps_scale, unsigned long long *d_counts);
 int gh_launch_scale_maps(gh_cuda_ctx *c, float *maps, int shell0, int nshells);
+int gh_launch_shell_extents(gh_cuda_ctx *c, int *ext_lo, int *ext_hi);
+int gh_launch_sparse_reduce(gh_cuda_ctx *c, const int *all_ext, float *out, int shell0, int nshells);
 int gh_launch_fastpath_audit(gh_cuda_ctx *c, const double *d_pos, const double *d_dz, long long n, float eps_scale,
                               unsigned long long *d_counts);
 int gh_launch_points(gh_cuda_ctx *c, const double *d_pos, const double *d_dz, long long n, int *d_shell,

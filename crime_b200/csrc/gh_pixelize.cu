@@ -405,6 +405,82 @@ __global__ void __launch_bounds__(256) scale_maps_kernel(float4 *__restrict__ ma
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Sparse map reduction over peer memory (opt-in, GH_SPARSE_REDUCE=1; several ranks with peer mappings).
+// A rank accumulates a contiguous range of z planes, so in every shell the pixels it touched lie in a band of
+// latitudes -- a contiguous interval of RING indices -- and most of its [n_nu][npix] stack is zero.  NCCL's
+// reduce-scatter moves (P-1)/P of the whole stack per rank regardless.  Instead: (1) every rank measures the
+// touched interval [lo, hi) of each shell of its own stack, (2) the intervals are all-gathered (which is also
+// the barrier that says everybody has finished accumulating), (3) the owner of a shell sums, pixel by pixel and
+// in rank order, exactly the peers' intervals that cover the pixel, reading them straight from the peers'
+// stacks over NVLink, applies the shell's temperature prefactor and writes its result.
+__global__ void __launch_bounds__(256) shell_extent_kernel(const float4 *__restrict__ maps, long long npix4,
+                                                           int *__restrict__ ext_lo, int *__restrict__ ext_hi)
+{
+  const int sh = blockIdx.y;
+  const float4 *m = maps + (size_t)sh * npix4;
+  // contiguous chunk per CTA: the first and last non-zero float4 of the chunk
+  const long long per = (npix4 + gridDim.x - 1) / gridDim.x;
+  const long long a = (long long)blockIdx.x * per, b = (a + per < npix4) ? a + per : npix4;
+  long long lo = npix4, hi = -1;
+  for (long long i = a + threadIdx.x; i < b; i += blockDim.x) {
+    const float4 v = __ldg(m + i);
+    if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
+      lo = (i < lo) ? i : lo;
+      hi = (i > hi) ? i : hi;
+    }
+  }
+  __shared__ long long s_lo[256], s_hi[256];
+  s_lo[threadIdx.x] = lo;
+  s_hi[threadIdx.x] = hi;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      s_lo[threadIdx.x] = min(s_lo[threadIdx.x], s_lo[threadIdx.x + o]);
+      s_hi[threadIdx.x] = max(s_hi[threadIdx.x], s_hi[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && s_hi[0] >= 0) {  // units: float4 index; hi exclusive
+    atomicMin(ext_lo + sh, (int)s_lo[0]);
+    atomicMax(ext_hi + sh, (int)s_hi[0] + 1);
+  }
+}
+
+struct MapPeers {
+  const float4 *m[GH_MAX_RANKS];
+};
+
+// all_ext: [rank][2][n_nu_pad] (lo then hi, float4 units).  One CTA = one chunk of one owned shell.
+__global__ void __launch_bounds__(256) sparse_reduce_kernel(MapPeers peers, const int *__restrict__ all_ext, int nranks,
+                                                            int n_nu_pad, long long npix4, int shell0,
+                                                            const double *__restrict__ prefac, float4 *__restrict__ out)
+{
+  const int sh = shell0 + blockIdx.y;
+  const double pf = prefac[sh];
+  __shared__ int s_lo[GH_MAX_RANKS], s_hi[GH_MAX_RANKS];
+  if ((int)threadIdx.x < nranks) {
+    s_lo[threadIdx.x] = all_ext[((size_t)threadIdx.x * 2 + 0) * n_nu_pad + sh];
+    s_hi[threadIdx.x] = all_ext[((size_t)threadIdx.x * 2 + 1) * n_nu_pad + sh];
+  }
+  __syncthreads();
+  float4 *o = out + (size_t)blockIdx.y * npix4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix4; i += (long long)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < nranks; ++q) {
+      if (i >= s_lo[q] && i < s_hi[q]) {
+        const float4 v = peers.m[q][(size_t)sh * npix4 + i];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    acc.x = (float)((double)acc.x * pf);  // src/pixelize.c:236-261, as scale_maps_kernel
+    acc.y = (float)((double)acc.y * pf);
+    acc.z = (float)((double)acc.z * pf);
+    acc.w = (float)((double)acc.w * pf);
+    o[i] = acc;
+  }
+}
+
 __global__ void __launch_bounds__(128) points_kernel(GhDev d, const double *__restrict__ pos, const double *__restrict__ dz,
                                                      long long n, int *__restrict__ shell, long long *__restrict__ pix)
 {
@@ -447,6 +523,33 @@ int gh_launch_scale_maps(gh_cuda_ctx *c, float *maps, int shell0, int nshells)
   if (bx > 1024) bx = 1024;
   dim3 grid(bx, nshells);
   scale_maps_kernel<<<grid, 256, 0, c->stream>>>(reinterpret_cast<float4 *>(maps), c->d_prefac, npix4, shell0);
+  GH_LAUNCH_CHECK(c);
+  return 0;
+}
+
+int gh_launch_shell_extents(gh_cuda_ctx *c, int *ext_lo, int *ext_hi)
+{
+  const long long npix4 = c->d.npix / 4;
+  int bx = (int)((npix4 + 256 * 64 - 1) / (256 * 64));  // >= 64 float4 per thread
+  if (bx < 1) bx = 1;
+  if (bx > 256) bx = 256;
+  dim3 grid(bx, c->d.n_nu_pad);
+  shell_extent_kernel<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const float4 *>(c->maps), npix4, ext_lo, ext_hi);
+  GH_LAUNCH_CHECK(c);
+  return 0;
+}
+
+int gh_launch_sparse_reduce(gh_cuda_ctx *c, const int *all_ext, float *out, int shell0, int nshells)
+{
+  if (nshells <= 0) return 0;
+  MapPeers mp;
+  for (int q = 0; q < GH_MAX_RANKS; ++q) mp.m[q] = (q < c->d.nranks) ? reinterpret_cast<const float4 *>(c->map_peers[q]) : nullptr;
+  const long long npix4 = c->d.npix / 4;
+  int bx = (int)((npix4 + 255) / 256);
+  if (bx > 1024) bx = 1024;
+  dim3 grid(bx, nshells);
+  sparse_reduce_kernel<<<grid, 256, 0, c->stream>>>(mp, all_ext, c->d.nranks, c->d.n_nu_pad, npix4, shell0, c->d_prefac,
+                                                   reinterpret_cast<float4 *>(out));
   GH_LAUNCH_CHECK(c);
   return 0;
 }

@@ -14,11 +14,13 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-# bounds: GH_MAP_BOUNDS, forced plane ranges for the map accumulation (None = the cost model's; "off" = own slabs).
+# bounds: GH_MAP_BOUNDS, forced plane ranges for the map accumulation (None = the cost model's; "off" = own slabs;
+# "sparse" = the cost model's ranges and GH_SPARSE_REDUCE=1).
 # The forced cases make rank 0 pull planes from above, rank 1 from below, in more than one staging chunk, and
 # leave one rank without any of its own planes.
 @pytest.mark.parametrize("world,n_grid,n_side,bounds", [(2, 64, 32, None), (2, 64, 32, "57"), (2, 64, 32, "9"), (2, 64, 32, "off"),
-                                                        (4, 128, 64, None), (4, 128, 64, "70,75,80"), (8, 128, 64, None)])
+                                                        (4, 128, 64, None), (4, 128, 64, "70,75,80"), (8, 128, 64, None),
+                                                        (2, 64, 32, "sparse"), (4, 128, 64, "sparse"), (8, 128, 64, "sparse")])
 def test_slab_decomposition_matches_single_gpu(world, n_grid, n_side, bounds):
     import os
     if _ngpu() < world:
@@ -26,6 +28,8 @@ def test_slab_decomposition_matches_single_gpu(world, n_grid, n_side, bounds):
     env = dict(os.environ)
     if bounds == "off":
         env["GH_NO_REBALANCE"] = "1"
+    elif bounds == "sparse":  # opt-in map reduction over peer memory instead of ncclReduceScatter
+        env["GH_SPARSE_REDUCE"] = "1"
     elif bounds:
         env["GH_MAP_BOUNDS"] = bounds
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
