@@ -255,6 +255,18 @@ static int apply_params(gh_cuda_ctx *c, const gh_cuda_params *p, int rank, int n
       d.sub_off[2 * GH_CUDA_N_SUBPART + i] = lcell * (g.uniform() - 0.5);
     }
     for (int i = 0; i < 3 * GH_CUDA_N_SUBPART; ++i) d.sub_off_f[i] = (float)d.sub_off[i];
+    for (int i = 0; i < GH_CUDA_N_SUBPART; ++i) {
+      const float ox = d.sub_off_f[i], oy = d.sub_off_f[GH_CUDA_N_SUBPART + i], oz = d.sub_off_f[2 * GH_CUDA_N_SUBPART + i];
+      float *m = d.sub_mono;
+      m[i] = ox * ox + oy * oy + oz * oz;
+      m[GH_CUDA_N_SUBPART + i] = ox * ox - oy * oy;
+      m[2 * GH_CUDA_N_SUBPART + i] = ox * oy;
+      m[3 * GH_CUDA_N_SUBPART + i] = ox * ox;
+      m[4 * GH_CUDA_N_SUBPART + i] = oy * oy;
+      m[5 * GH_CUDA_N_SUBPART + i] = oz * oz;
+      m[6 * GH_CUDA_N_SUBPART + i] = ox * oz;
+      m[7 * GH_CUDA_N_SUBPART + i] = oy * oz;
+    }
   }
   {
     // src/pixelize.c:155,246-256
@@ -502,6 +514,7 @@ extern "C" int gh_cuda_create(const gh_cuda_params *p, int rank, int nranks, con
   } while (0)
 
   CREATE_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->acc_taylor = getenv("GH_ACC_TAYLOR") != nullptr;  // experimental, see accumulate_kernel
   // one rank only for now: the fused pass has not been through the multi-GPU parity run yet
   c->fuse_vel = nranks == 1 && getenv("GH_NO_FUSE_VEL") == nullptr;
   CREATE_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));

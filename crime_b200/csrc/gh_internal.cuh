@@ -40,6 +40,9 @@ struct GhDev {
   double z_lo_cull, z_hi_cull; // redshift window outside of which no sub-particle can land in a shell
   double sub_off[3 * GH_CUDA_N_SUBPART];
   float sub_off_f[3 * GH_CUDA_N_SUBPART];
+  // monomials of the float offsets for the per-cell Taylor pixelisation (GH_ACC_TAYLOR): |o|^2, ox^2-oy^2, ox*oy,
+  // ox^2, oy^2, oz^2, ox*oz, oy*oz
+  float sub_mono[8 * GH_CUDA_N_SUBPART];
 };
 
 #define GH_MAX_RANKS 16
@@ -71,6 +74,7 @@ struct gh_cuda_ctx {
   ncclComm_t comm;
   bool have_comm;
   bool have_peers;                 // peer mappings established (nranks>1, same node)
+  bool acc_taylor;                 // opt-in (GH_ACC_TAYLOR=1): per-cell Taylor pixelisation in the equatorial belt
   bool fuse_vel;                   // gh_cuda_run*: radial velocity and get_HI in one pass
   bool sparse_reduce;              // opt-in: map reduction by pulling the peers' touched pixel intervals (GH_SPARSE_REDUCE=1)
   float *map_peers[GH_MAX_RANKS];  // every rank's accumulation stack (peer-mapped), sparse_reduce only

@@ -217,7 +217,14 @@ __device__ __forceinline__ bool fast_pixel(const FastCtx &f, float cth, float tt
 // Planes: the launch covers gridDim.z consecutive planes; plane blockIdx.z sits at local index iz_base +
 // blockIdx.z of the buffers passed in and is global plane zg_base + blockIdx.z (this rank's own slab, or planes
 // pulled from a neighbour for load balance -- see enqueue_maps in gh_api.cu).
-template <bool AUDIT>
+// TAYLOR (opt-in, GH_ACC_TAYLOR=1; written after this round's GPU budget was spent -- not yet audited on hardware):
+// cells whose sub-particles all lie in HEALPix's equatorial belt get the two ring coordinates
+// A = ns*(tt + 1/2) and B = (3/4) ns cos(theta) from a second-order Taylor expansion about the cell centre.  The
+// ten offsets are the same for every cell, so their monomials are constants and a sub-particle costs 4 + 9 FMAs
+// for (A, B) and 3 for r^2, instead of positions, rsqrt, the azimuth series and cos(theta).  The third-order
+// remainder, <= ns*(0.2123 (d/rho)^3 + 0.375 (d/r)^3) with d the half cell diagonal (tools/taylor_proto.py), is
+// added to the confidence margin of the cell.
+template <bool AUDIT, bool TAYLOR>
 __global__ void __launch_bounds__(128) accumulate_kernel(GhDev d, const float *__restrict__ mass,
                                                          const float *__restrict__ dzrsd, float *__restrict__ maps,
                                                          float eps_scale, unsigned long long *__restrict__ counts,
@@ -272,6 +279,75 @@ __global__ void __launch_bounds__(128) accumulate_kernel(GhDev d, const float *_
       const bool series = rp2 > 576.0f * (float)(d.dx * d.dx);
       const float phi_c = atan2f(yh, xh);
       const CellShells cs = cell_shells(f, zs_lo, zs_hi, dzf);
+      bool lean = false;
+      if constexpr (TAYLOR) {
+        const float inv_rc = rsqrt_ftz(fmaf(zh, zh, rp2));
+        // every sub-particle of the cell in the equatorial belt (|d cos(theta)| <= d/r), away from the tt wrap,
+        // and the cell's shells known as r^2 thresholds
+        lean = cs.ok && series && (fabsf(zh) * inv_rc + h * inv_rc < f.cth_lo) && (fabsf(yh) > 2.0f * h || xh < 0.f);
+        if (lean) {
+          const float fns = f.fns, irho2 = rcp_ftz(rp2), ir2 = inv_rc * inv_rc, ir3 = inv_rc * ir2, ir5 = ir3 * ir2;
+          const float k = 0.63661977236758134308f * fns, kq = k * irho2 * irho2, c34 = 0.75f * fns;
+          float ttc = phi_c * 0.63661977236758134308f;
+          ttc += (ttc < 0.f) ? 4.0f : 0.f;
+          const float Ax = -k * yh * irho2, Ay = k * xh * irho2;
+          const float Axx = kq * xh * yh, Axy = kq * fmaf(yh, yh, -xh * xh);
+          const float A0 = fmaf(Ax, xl, fmaf(Ay, yl, fmaf(fns, ttc, 0.5f * fns)));
+          const float zi3 = zh * ir3, t3 = 3.0f * zh * ir5;
+          const float Bx = -c34 * xh * zi3, By = -c34 * yh * zi3, Bz = c34 * rp2 * ir3;
+          const float Bxx = 0.5f * c34 * fmaf(t3 * xh, xh, -zi3), Byy = 0.5f * c34 * fmaf(t3 * yh, yh, -zi3);
+          const float Bzz = 0.5f * c34 * fmaf(t3 * zh, zh, -3.0f * zi3);
+          const float Bxy = c34 * t3 * xh * yh, Bxz = c34 * fmaf(t3 * xh, zh, -xh * ir3), Byz = c34 * fmaf(t3 * yh, zh, -yh * ir3);
+          const float B0 = fmaf(Bx, xl, fmaf(By, yl, fmaf(Bz, zl, c34 * zh * inv_rc)));
+          const float r2c = fmaf(2.0f * xh, xl, fmaf(2.0f * yh, yl, fmaf(2.0f * zh, zl, fmaf(zh, zh, rp2))));
+          const float x2 = 2.0f * xh, y2 = 2.0f * yh, z2 = 2.0f * zh;
+          // third-order remainder of both expansions (h = half cell diagonal + slack), on top of the fp32 margin
+          const float dr = h * inv_rc, drho = h * rsqrt_ftz(rp2);
+          const float e_cell = f.eidx + fns * fmaf(0.2123f * drho, drho * drho, 0.375f * dr * dr * dr);
+          const float m_lo = e_cell, m_hi = 1.0f - e_cell;
+          const float a_lo = 0.5f * fns + fns * f.eps_tt + e_cell, a_hi = 4.5f * fns - fns * f.eps_tt - e_cell;
+          const int ns = f.ns;
+          const float *M = d.sub_mono;
+#pragma unroll 2
+          for (int isub = 0; isub < GH_CUDA_N_SUBPART; ++isub) {
+            const float ox = d.sub_off_f[isub], oy = d.sub_off_f[GH_CUDA_N_SUBPART + isub], oz = d.sub_off_f[2 * GH_CUDA_N_SUBPART + isub];
+            const float r2 = r2c + fmaf(x2, ox, fmaf(y2, oy, fmaf(z2, oz, M[isub])));
+            const bool in0 = r2 < cs.lo_a, in1 = (r2 > cs.hi_a) & (r2 < cs.lo_b), in2 = r2 > cs.hi_b;
+            int inu = in0 ? cs.shell[0] : (in1 ? cs.shell[1] : cs.shell[2]);
+            int st = (in0 | in1 | in2) ? (inu >= 0 ? GH_FAST_IN : GH_FAST_OUT) : GH_FAST_UNSURE;
+            int pix = -1;
+            if (st == GH_FAST_IN) {
+              const float A = fmaf(Ax, ox, fmaf(Ay, oy, fmaf(Axx, M[GH_CUDA_N_SUBPART + isub], fmaf(Axy, M[2 * GH_CUDA_N_SUBPART + isub], A0))));
+              const float B = fmaf(Bx, ox, fmaf(By, oy, fmaf(Bz, oz, fmaf(Bxx, M[3 * GH_CUDA_N_SUBPART + isub],
+                              fmaf(Byy, M[4 * GH_CUDA_N_SUBPART + isub], fmaf(Bzz, M[5 * GH_CUDA_N_SUBPART + isub],
+                              fmaf(Bxy, M[2 * GH_CUDA_N_SUBPART + isub], fmaf(Bxz, M[6 * GH_CUDA_N_SUBPART + isub],
+                              fmaf(Byz, M[7 * GH_CUDA_N_SUBPART + isub], B0)))))))));
+              const float a = A - B, b = A + B;
+              const float fa = floorf(a), fb = floorf(b);
+              const float ra = a - fa, rb = b - fb;
+              const bool ok = (ra > m_lo) & (ra < m_hi) & (rb > m_lo) & (rb < m_hi) & (A > a_lo) & (A < a_hi);
+              const int jp = (int)fa, jm = (int)fb;
+              const int ir = ns + 1 + jp - jm;
+              int ip = (jp + jm - ns + 2 - (ir & 1)) >> 1;
+              ip -= (ip >= 4 * ns) ? 4 * ns : 0;
+              pix = 2 * ns * (ns - 1) + (ir - 1) * 4 * ns + ip;
+              if (!ok) st = GH_FAST_UNSURE;
+            }
+            if (!AUDIT) {
+              if (st == GH_FAST_IN) atomicAdd(maps + ((size_t)d.npix * inu + pix), w);
+              else if (st == GH_FAST_UNSURE) need |= 1u << isub;
+            } else {
+              long long pe;
+              const int se = gh_point_to_shell_pixel(t, x0 + d.sub_off[isub], y0 + d.sub_off[GH_CUDA_N_SUBPART + isub],
+                                                     z0 + d.sub_off[2 * GH_CUDA_N_SUBPART + isub], (double)dzf, &pe);
+              if (st == GH_FAST_OUT) { c_out++; if (pe >= 0) c_wrong++; }
+              else if (st == GH_FAST_IN) { c_in++; if (inu != se || (long long)pix != pe) c_wrong++; }
+              else c_unsure++;
+            }
+          }
+        }
+      }
+      if (!lean) {
 #pragma unroll 2
       for (int isub = 0; isub < GH_CUDA_N_SUBPART; ++isub) {
         const float ox = xl + d.sub_off_f[isub], oy = yl + d.sub_off_f[GH_CUDA_N_SUBPART + isub];
@@ -313,6 +389,7 @@ __global__ void __launch_bounds__(128) accumulate_kernel(GhDev d, const float *_
           else if (st == GH_FAST_IN) { c_in++; if (inu != se || (long long)pix != pe) c_wrong++; }
           else c_unsure++;
         }
+      }
       }
     }
   }
@@ -500,7 +577,8 @@ int gh_launch_accumulate(gh_cuda_ctx *c, const float *mass, const float *dzrsd, 
   const GhDev &d = c->d;
   if (nplanes <= 0) return 0;
   dim3 grid((d.n + 7) / 8, (d.n + 15) / 16, nplanes), block(8, 16);
-  accumulate_kernel<false><<<grid, block, 0, c->stream>>>(d, mass, dzrsd, c->maps, 1.0f, nullptr, iz_base, zg_base);
+  if (c->acc_taylor) accumulate_kernel<false, true><<<grid, block, 0, c->stream>>>(d, mass, dzrsd, c->maps, 1.0f, nullptr, iz_base, zg_base);
+  else accumulate_kernel<false, false><<<grid, block, 0, c->stream>>>(d, mass, dzrsd, c->maps, 1.0f, nullptr, iz_base, zg_base);
   GH_LAUNCH_CHECK(c);
   return 0;
 }
@@ -509,8 +587,9 @@ int gh_launch_accumulate_audit(gh_cuda_ctx *c, float eps_scale, unsigned long lo
 {
   const GhDev &d = c->d;
   dim3 grid((d.n + 7) / 8, (d.n + 15) / 16, d.nz_here), block(8, 16);
-  accumulate_kernel<true><<<grid, block, 0, c->stream>>>(d, reinterpret_cast<const float *>(c->gridA),
-                                                       reinterpret_cast<const float *>(c->gridC), c->maps, eps_scale, d_counts, 0, d.iz0);
+  const float *m = reinterpret_cast<const float *>(c->gridA), *z = reinterpret_cast<const float *>(c->gridC);
+  if (c->acc_taylor) accumulate_kernel<true, true><<<grid, block, 0, c->stream>>>(d, m, z, c->maps, eps_scale, d_counts, 0, d.iz0);
+  else accumulate_kernel<true, false><<<grid, block, 0, c->stream>>>(d, m, z, c->maps, eps_scale, d_counts, 0, d.iz0);
   GH_LAUNCH_CHECK(c);
   return 0;
 }

@@ -515,3 +515,20 @@ def test_full_size_properties_512(tables_nu64):
         assert np.array_equal(a2 != 0, a1 != 0)
         nz = a1 != 0
         assert np.abs(a2[nz] / (2.0 * a1[nz]) - 1).max() < 1e-5
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("GH_TEST_EXPERIMENTAL"), reason="opt-in variants not yet validated on hardware")
+def test_experimental_taylor_pixelisation_audit(tables_nu64):
+    """GH_ACC_TAYLOR=1 (per-cell Taylor expansion of the ring coordinates in the equatorial belt): the on-device
+    audit must find no disagreement with the exact path, also with the margins halved.  Run with
+    GH_TEST_EXPERIMENTAL=1 GH_ACC_TAYLOR=1; not part of the default suite until it has been."""
+    import os
+    from crime_b200 import GetHI, params_from_tables
+    assert os.environ.get("GH_ACC_TAYLOR"), "set GH_ACC_TAYLOR=1 together with GH_TEST_EXPERIMENTAL=1"
+    p = params_from_tables(tables_nu64, n_grid=256, n_side=256, seed=3)
+    with GetHI(p) as g:
+        g.create_d_and_vr_fields(); g.get_HI()
+        for scale in (1.0, 0.5):
+            a = g.accumulate_audit(scale)
+            assert a["wrong"] == 0, a
+            assert a["unsure"] < 0.03 * (a["inside"] + a["unsure"]), a
