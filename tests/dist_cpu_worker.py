@@ -22,13 +22,14 @@ from oracle.binding import Oracle, Slab, _ptr  # noqa: E402
 import ctypes as C  # noqa: E402
 
 
-def run(rank: int, world: int, n: int, n_side: int, out_dir: str):
+def run(rank: int, world: int, n: int, n_side: int, out_dir: str, obs_z: float = 0.5):
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29533")
     dist.init_process_group("gloo", rank=rank, world_size=world)
     orc = Oracle()
     tables = dict(np.load(ROOT / "tests" / "golden" / "ref_tables_nu64.npz"))
     p = params_from_tables(tables, n_grid=n, n_side=n_side, seed=99)
+    p.pos_obs[2] = obs_z * p.l_box   # an off-centre observer makes the equal-cost plane ranges differ from the slabs
     nh = n // 2 + 1
     nz, iz0 = slab.slab_bounds(n, world, rank)
     # (1) k-space for this rank's ky rows, layout [kz][ky_local][kx]
@@ -67,20 +68,31 @@ def run(rank: int, world: int, n: int, n_side: int, out_dir: str):
     dist.all_reduce(t)
     sigma2 = float(t[1] - t[0] * t[0])
     mass, dz = orc.get_HI(p, sigma2, dens, rvel, iz0)
-    # (7) maps: full per-rank stack, reduce-scatter over padded shells
+    # (7) maps: this rank accumulates the plane range the library's cost model gives it
+    # (gh_cuda_map_plane_bounds); planes outside its slab are pulled from their owner (on GPUs: peer copies over
+    # NVLink, here: an all-gather of the slabs); full per-rank stack, reduce-scatter over padded shells
     nsh, s0, npad = slab.shell_bounds(p.n_nu, world, rank)
     npix = 12 * n_side * n_side
     stack = np.zeros((npad, npix), np.float32)
-    orc.accumulate_maps(p, mass, dz, iz0, stack[:p.n_nu])
+    lo_p, hi_p = slab.map_plane_ranges(p, world)[rank]
+    gm = [torch.empty(nz, n, 2 * nh) for _ in range(world)]
+    gz = [torch.empty(nz, n, 2 * nh) for _ in range(world)]
+    dist.all_gather(gm, torch.from_numpy(np.ascontiguousarray(mass)))
+    dist.all_gather(gz, torch.from_numpy(np.ascontiguousarray(dz)))
+    all_m, all_z = torch.cat(gm).numpy(), torch.cat(gz).numpy()
+    if hi_p > lo_p:
+        orc.accumulate_maps(p, np.ascontiguousarray(all_m[lo_p:hi_p]), np.ascontiguousarray(all_z[lo_p:hi_p]), lo_p, stack[:p.n_nu])
     mine = torch.empty(npad // world, npix)
     dist.reduce_scatter_tensor(mine, torch.from_numpy(stack))
     mine = mine.numpy()[:nsh]
     pref = orc.shell_prefactors(p)[s0:s0 + nsh]
     mine = (mine.astype(np.float64) * pref[:, None]).astype(np.float32)
-    np.savez(f"{out_dir}/rank{rank}.npz", dens=dens, rvel=rvel, mass=mass, maps=mine, sigma2=sigma2, iz0=iz0, s0=s0)
+    np.savez(f"{out_dir}/rank{rank}.npz", dens=dens, rvel=rvel, mass=mass, maps=mine, sigma2=sigma2, iz0=iz0, s0=s0,
+             plane_range=np.array([lo_p, hi_p]))
     dist.barrier()
     dist.destroy_process_group()
 
 
 if __name__ == "__main__":
-    run(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5])
+    run(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5],
+        float(sys.argv[6]) if len(sys.argv) > 6 else 0.5)
