@@ -532,3 +532,33 @@ def test_experimental_taylor_pixelisation_audit(tables_nu64):
             a = g.accumulate_audit(scale)
             assert a["wrong"] == 0, a
             assert a["unsure"] < 0.03 * (a["inside"] + a["unsure"]), a
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("GH_TEST_EXPERIMENTAL"), reason="linked after the round's GPU budget was spent; not yet run on hardware")
+def test_reference_own_driver_on_the_gpu_path(tmp_path):
+    """oracle/_ref/GetHI_gpu: the reference's own driver, parameter reader, cosmology and FITS writer with its hot
+    path replaced by libgh_cuda.so through the glue of INTEGRATION.md.  Its maps must equal what the Python
+    binding produces from the reference's own tables for the same parameter file."""
+    import subprocess
+    from pathlib import Path
+    from crime_b200 import GetHI, host
+    from oracle.binding import Reference, write_nutable, write_param_file
+    root = Path(__file__).resolve().parents[1]
+    exe = root / "oracle" / "_ref" / "GetHI_gpu"
+    if not exe.exists() or not Reference.available():
+        pytest.skip("oracle/_ref not built")
+    write_nutable(tmp_path / "nu.txt", 10)
+    write_param_file(tmp_path / "p.ini", n_grid=64, n_side=16, nutable=tmp_path / "nu.txt",
+                     pk_file=root / "data" / "Pk_synth.dat", prefix=tmp_path / "drop", seed=21)
+    r = subprocess.run([str(exe), str(tmp_path / "p.ini")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    ref = Reference()
+    p = ref.params(ref.read_run_params(tmp_path / "p.ini"))
+    with GetHI(p) as g:
+        maps = g.run().copy()
+    for s in range(10):
+        m, _ = host.read_healpix_map(tmp_path / f"drop_{s + 1:03d}.fits")
+        assert np.array_equal(m != 0, maps[s] != 0)
+        nz = maps[s] != 0
+        if nz.any():
+            assert np.abs(m[nz] / maps[s][nz] - 1).max() < 1e-5
