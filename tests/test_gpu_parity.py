@@ -562,3 +562,49 @@ def test_reference_own_driver_on_the_gpu_path(tmp_path):
         nz = maps[s] != 0
         if nz.any():
             assert np.abs(m[nz] / maps[s][nz] - 1).max() < 1e-5
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("GH_TEST_LARGE"), reason="large-grid checks (tens of GB of host memory, minutes of CPU): GH_TEST_LARGE=1")
+@pytest.mark.parametrize("n", [512, 1024])
+def test_fft_large_grids_against_pocketfft(tables_nu64, n):
+    """The FFT kernels are instantiated per line length with their own tile widths and radix plans (512: W=16, 8*8*8;
+    1024: W=8 strided / 16 rows, 8*8*4*4).  Whole-field comparison with scipy's float32 c2r (same semantics as the
+    oracle's, checked on the CPU at small sizes) for the lengths the BASELINE configurations use on one GPU."""
+    import scipy.fft
+    from crime_b200 import GetHI, params_from_tables
+    from crime_b200.abi import GRID_DENS
+    p = params_from_tables(tables_nu64, n_grid=n, n_side=16, seed=3)
+    with GetHI(p) as g:
+        g.generate_k()
+        dk, _ = g.download_delta_k()
+        g.fft_fields()
+        dens = g.download_grid(GRID_DENS)[:, :, :n]
+    norm = (np.sqrt(2 * np.pi) / p.l_box) ** 3 * float(n) ** 3
+    ref = scipy.fft.irfftn(dk, s=(n, n, n), axes=(0, 1, 2), workers=-1)
+    ref *= np.float32(norm)
+    assert field_err(dens, ref) < 2 * TOL       # two float32 transforms against each other
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("GH_TEST_LARGE"), reason="large-grid checks: GH_TEST_LARGE=1")
+def test_fft_2048_variance_against_the_input_spectrum(tables_nu150):
+    """2048^3 on one GPU (103 GiB of grids): the variance of the transformed field against the sum of the mode
+    variances -- a wrong radix plan, twiddle or digit reversal in the 2048-point instantiations destroys it."""
+    from crime_b200 import GetHI, params_from_tables
+    n = 2048
+    p = params_from_tables(tables_nu150, n_grid=n, n_side=16, seed=3)
+    with GetHI(p) as g:
+        s2 = g.create_d_and_vr_fields()
+    dk = 2 * np.pi / p.l_box
+    idx = np.fft.fftfreq(n, 1.0 / n)
+    logk, pk = tables_nu150["logkarr"], tables_nu150["pkarr"]
+    ky, kx = np.meshgrid(idx, np.arange(n // 2 + 1), indexing="ij")
+    wgt = np.where((kx == 0) | (kx == n // 2), 0.5, 2.0)
+    expected = 0.0
+    for kz in idx:
+        k2 = (kx ** 2 + ky ** 2 + kz ** 2) * dk * dk
+        lg = 0.5 * np.log10(np.where(k2 > 0, k2, 1.0))
+        ik = np.clip(((lg - p.logkmin) * p.idlogk).astype(int), 0, p.numk - 2)
+        pkv = pk[ik] + (lg - logk[ik]) * (pk[ik + 1] - pk[ik]) * p.idlogk
+        expected += (np.where(k2 > 0, pkv / dk ** 3 * np.exp(-p.r2_smooth * k2), 0.0) * wgt).sum()
+    expected *= (np.sqrt(2 * np.pi) / p.l_box) ** 6
+    assert abs(s2 / expected - 1) < 0.01
