@@ -392,6 +392,19 @@ def main():
         allt = [torch.zeros_like(tt) for _ in range(world)]
         dist.all_gather(allt, tt)
         per_rank = [{k: round(float(v), 3) for k, v in zip(abi.STAGE_NAMES, a.tolist())} for a in allt]
+    nvlink = None
+    if world > 1:
+        # opt-in (GH_TIME_FFT_PASSES=1): the z passes carry the transposes; every rank pushes (P-1)/P of its slab of each
+        # field to its peers inside them.  Slowest rank's time, so the figure is the all-to-all's, not one link's.
+        zt = torch.tensor(list(g.fft_pass_times()), device=dev, dtype=torch.float64)
+        dist.all_reduce(zt, op=dist.ReduceOp.MAX)
+        z_ms = [float(v) for v in zt.tolist()]
+        if min(z_ms) > 0:
+            sent = (world - 1) / world * (cells / world) * (1 + 2.0 / n_grid) * 4.0   # bytes per rank per field
+            ach = 2 * sent / (sum(z_ms) * 1e-3) / 1e9
+            nvlink = {"achieved": ach, "peak": 900.0, "unit": "GB/s per GPU per direction", "frac": ach / 900.0,
+                      "z_pass_ms": z_ms, "bytes_sent_per_rank_per_field": sent,
+                      "what": "transpose fused into the FFT z pass (peer stores), incl. the closing barrier; peak = NVLink 5 nominal"}
     n_here = g.n_shells_here
     table_bytes = sum(np.asarray(v).nbytes for k, v in tables.items() if k in abi.TABLE_FIELDS)
     maps_bytes = n_here * g.npix * 4
@@ -421,6 +434,8 @@ def main():
         }
         if per_rank is not None:
             line["stage_ms_by_rank"] = per_rank
+        if nvlink is not None:
+            line["nvlink"] = nvlink
         if not args.no_cpu_baseline and world == 1:
             sg = args.cpu_grid or min(n_grid, 256)
             try:

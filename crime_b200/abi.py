@@ -117,6 +117,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         "gh_cuda_destroy": ([vp], i32),
         "gh_cuda_slab": ([vp, C.POINTER(i32), C.POINTER(i32)], i32),
         "gh_cuda_shells": ([vp, C.POINTER(i32), C.POINTER(i32)], i32),
+        "gh_cuda_fft_pass_times": ([vp, f64p], i32),
         "gh_cuda_map_plane_bounds": ([C.POINTER(GhCudaParams), i32, C.POINTER(i32)], i32),
         "gh_cuda_create_d_and_vr_fields": ([vp, f64p, f64p], i32),
         "gh_cuda_get_HI": ([vp], i32),
@@ -162,7 +163,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
 
 EXPORTED_SYMBOLS = (
     "gh_cuda_get_unique_id", "gh_cuda_create", "gh_cuda_set_params", "gh_cuda_destroy", "gh_cuda_slab", "gh_cuda_shells",
-    "gh_cuda_map_plane_bounds",
+    "gh_cuda_map_plane_bounds", "gh_cuda_fft_pass_times",
     "gh_cuda_create_d_and_vr_fields", "gh_cuda_get_HI", "gh_cuda_mk_T_maps", "gh_cuda_mk_T_maps_begin", "gh_cuda_wait_shells", "gh_cuda_run", "gh_cuda_run_async", "gh_cuda_wait",
     "gh_cuda_host_alloc", "gh_cuda_host_free", "gh_cuda_generate_k", "gh_cuda_fft_fields",
     "gh_cuda_radial_velocity", "gh_cuda_sigma_dens", "gh_cuda_accumulate_maps", "gh_cuda_synchronize",

@@ -449,6 +449,9 @@ extern "C" int gh_cuda_destroy(gh_cuda_ctx *c)
   if (c->pull_stream) { cudaStreamSynchronize(c->pull_stream); cudaStreamDestroy(c->pull_stream); }
   for (int i = 0; i < GH_MAX_CHUNKS; ++i)
     if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
+  for (int f = 0; f < 2; ++f)
+    for (int k = 0; k < 2; ++k)
+      if (c->ev_pass[f][k]) cudaEventDestroy(c->ev_pass[f][k]);
   if (c->ev_bar) cudaEventDestroy(c->ev_bar);
   if (c->ev_pulled) cudaEventDestroy(c->ev_pulled);
   if (c->ev_chunk_free) cudaEventDestroy(c->ev_chunk_free);
@@ -515,6 +518,11 @@ extern "C" int gh_cuda_create(const gh_cuda_params *p, int rank, int nranks, con
 
   CREATE_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   c->acc_taylor = getenv("GH_ACC_TAYLOR") != nullptr;  // experimental, see accumulate_kernel
+  if (getenv("GH_TIME_FFT_PASSES")) {
+    for (int f = 0; f < 2; ++f)
+      for (int k = 0; k < 2; ++k) CREATE_OK(cudaEventCreate(&c->ev_pass[f][k]));
+    c->time_fft_passes = true;
+  }
   // one rank only for now: the fused pass has not been through the multi-GPU parity run yet
   c->fuse_vel = nranks == 1 && getenv("GH_NO_FUSE_VEL") == nullptr;
   CREATE_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -647,6 +655,24 @@ extern "C" int gh_cuda_synchronize(gh_cuda_ctx *c)
 }
 
 extern "C" void *gh_cuda_stream(const gh_cuda_ctx *c) { return c ? (void *)c->stream : nullptr; }
+// Opt-in (GH_TIME_FFT_PASSES=1 at context creation): device time of each field's z pass including, on several
+// ranks, the transpose fused into it and the barrier that closes it.  z_ms[0] = density, z_ms[1] = potential;
+// -1 when the timers are off or no FFT has run.  Synchronises the stream.
+extern "C" int gh_cuda_fft_pass_times(gh_cuda_ctx *c, double *z_ms)
+{
+  GH_CTX(c);
+  GH_REQUIRE(z_ms, "gh_cuda_fft_pass_times: null output");
+  z_ms[0] = z_ms[1] = -1.0;
+  if (!c->time_fft_passes) return 0;
+  GH_CUDA_OK(cudaStreamSynchronize(c->stream));
+  for (int f = 0; f < 2; ++f) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev_pass[f][0], c->ev_pass[f][1]) == cudaSuccess) z_ms[f] = ms;
+    else (void)cudaGetLastError();
+  }
+  return 0;
+}
+
 extern "C" unsigned long long gh_cuda_kernel_launches(const gh_cuda_ctx *c) { return c ? c->launches : 0ULL; }
 
 extern "C" int gh_cuda_host_alloc(void **ptr, unsigned long long bytes)

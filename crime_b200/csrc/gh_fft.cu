@@ -391,6 +391,7 @@ int fft_field(gh_cuda_ctx *c, float2 *field)
     g.peer_chunk = (long long)d.nz_here * d.nky_here * nh;
     // peers must be done with their receive buffers (previous field's y pass, previous realisation's maps)
     if (g.peer_mode && gh_stream_barrier(c)) return 1;
+    if (c->time_fft_passes) cudaEventRecord(c->ev_pass[field == c->gridA ? 0 : 1][0], c->stream);
     if (launch_strided<N, WSEL, NTSEL>(c, field, field, g, 1)) return 1;
   }
   const float2 *ysrc = field;
@@ -414,6 +415,7 @@ int fft_field(gh_cuda_ctx *c, float2 *field)
       }
       GH_NCCL_OK(ncclGroupEnd());
     }
+    if (c->time_fft_passes) cudaEventRecord(c->ev_pass[field == c->gridA ? 0 : 1][1], c->stream);
     // received layout [q][z_local][ky_local][kx]; ky = q*nky_here + ky_local
     ysrc = c->gridC;
     g.src_group_stride = (long long)d.nky_here * nh;
@@ -421,6 +423,7 @@ int fft_field(gh_cuda_ctx *c, float2 *field)
     g.blk_shift = ilog2(d.nky_here);
     g.src_chunk = (long long)chunk;
   } else {
+    if (c->time_fft_passes) cudaEventRecord(c->ev_pass[field == c->gridA ? 0 : 1][1], c->stream);
     g.src_group_stride = (long long)d.n * nh;
     g.src_stride = nh;
     g.blk_shift = 30;

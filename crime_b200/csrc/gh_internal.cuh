@@ -74,6 +74,8 @@ struct gh_cuda_ctx {
   ncclComm_t comm;
   bool have_comm;
   bool have_peers;                 // peer mappings established (nranks>1, same node)
+  bool time_fft_passes;            // opt-in (GH_TIME_FFT_PASSES=1): events around each field's z pass + transpose
+  cudaEvent_t ev_pass[2][2];
   bool acc_taylor;                 // opt-in (GH_ACC_TAYLOR=1): per-cell Taylor pixelisation in the equatorial belt
   bool fuse_vel;                   // gh_cuda_run*: radial velocity and get_HI in one pass
   bool sparse_reduce;              // opt-in: map reduction by pulling the peers' touched pixel intervals (GH_SPARSE_REDUCE=1)

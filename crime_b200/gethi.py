@@ -252,6 +252,12 @@ class GetHI:
         self._check(self.lib.gh_cuda_stage_times(self._ctx, ms))
         return dict(zip(STAGE_NAMES, list(ms)))
 
+    def fft_pass_times(self) -> tuple[float, float]:
+        """ms of the density / potential z pass incl. the fused transpose (-1: GH_TIME_FFT_PASSES was not set)."""
+        ms = (C.c_double * 2)()
+        self._check(self.lib.gh_cuda_fft_pass_times(self._ctx, ms))
+        return float(ms[0]), float(ms[1])
+
     def kernel_launches(self) -> int:
         return int(self.lib.gh_cuda_kernel_launches(self._ctx))
 

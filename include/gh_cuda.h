@@ -207,6 +207,12 @@ int gh_cuda_accumulate_audit(gh_cuda_ctx *ctx, double eps_scale, unsigned long l
 
 /* per-stage device times of the most recent calls, GH_T_NSLOTS doubles in ms */
 int gh_cuda_stage_times(gh_cuda_ctx *ctx, double *ms_out);
+/* Opt-in timers (GH_TIME_FFT_PASSES=1 in the environment when the context is created): device milliseconds of
+ * each field's z pass, which on several GPUs includes the transpose fused into it (peer stores over NVLink) and
+ * the barrier that closes it -- the interval the NVLink fraction of the roofline is computed from.
+ * z_ms[0] = density, z_ms[1] = velocity potential; -1 when off. */
+int gh_cuda_fft_pass_times(gh_cuda_ctx *ctx, double *z_ms);
+
 /* launches of our own kernels issued by this context since creation */
 unsigned long long gh_cuda_kernel_launches(const gh_cuda_ctx *ctx);
 /* the CUDA stream (cudaStream_t as void*) all work of this context is enqueued on */
