@@ -393,7 +393,7 @@ def main():
         dist.all_gather(allt, tt)
         per_rank = [{k: round(float(v), 3) for k, v in zip(abi.STAGE_NAMES, a.tolist())} for a in allt]
     nvlink = None
-    if world > 1:
+    if world > 1 and os.environ.get("GH_TIME_FFT_PASSES"):
         # opt-in (GH_TIME_FFT_PASSES=1): the z passes carry the transposes; every rank pushes (P-1)/P of its slab of each
         # field to its peers inside them.  Slowest rank's time, so the figure is the all-to-all's, not one link's.
         zt = torch.tensor(list(g.fft_pass_times()), device=dev, dtype=torch.float64)
