@@ -41,9 +41,15 @@ def main():
     g.get_HI()
     mass = g.download_grid(GRID_DENS)
     maps = g.mk_T_maps().copy()
+    # the one-call path (gh_cuda_run: its own stage order, fused passes where enabled) must give the same maps
+    maps_run = g.run().copy()
+    run_ok = bool(np.array_equal(maps_run != 0, maps != 0))
+    if run_ok and (maps != 0).any():
+        run_ok = bool(np.abs(maps_run[maps != 0] / maps[maps != 0] - 1).max() < 1e-5)
     shells = (g.shell0_here, g.n_shells_here)
     gathered = [None] * world if rank == 0 else None
-    dist.gather_object(dict(slabs=slabs, dk=dk, mass=mass, maps=maps, shells=shells, s2=s2, iz0=g.iz0_here), gathered, 0)
+    dist.gather_object(dict(slabs=slabs, dk=dk, mass=mass, maps=maps, shells=shells, s2=s2, iz0=g.iz0_here, run_ok=run_ok),
+                       gathered, 0)
     g.end_fftw()
     ok = True
     if rank == 0:
@@ -75,6 +81,8 @@ def main():
             nzm = b != 0
             if nzm.any() and np.abs(a[nzm] / b[nzm] - 1).max() > 1e-5:
                 print(f"rank {r}: map values differ {np.abs(a[nzm] / b[nzm] - 1).max():.3e}"); ok = False
+            if not part["run_ok"]:
+                print(f"rank {r}: gh_cuda_run's maps differ from the staged calls'"); ok = False
             if abs(part["s2"] - s2_one) > 1e-12 * s2_one:
                 print(f"rank {r}: sigma2 {part['s2']} vs {s2_one}"); ok = False
         # the k-space realisation does not depend on the number of slabs
