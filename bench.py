@@ -7,12 +7,15 @@ for the GPU count:  1 GPU: 512^3, nside 256, 64 shells;  2/4 GPUs: 1024^3, nside
 8 GPUs: 2048^3, nside 1024, 150 shells (override with --grid/--nside/--shells).
 
   value : cells / device time with the run parameters already resident on the device and the maps left
-          on the device (CUDA events on the library's stream, max over ranks)
-  e2e   : the same through the reference-facing C-ABI with HOST buffers: parameter tables sent from host
-          memory and this rank's finished maps copied back into pinned host memory inside the timed region
+          on the device (CUDA events on the library's stream, max over ranks) -- the device-resident figure
+  e2e   : THE HEADLINE: the same through the reference-facing C-ABI with HOST buffers: parameter tables sent from
+          host memory and this rank's finished maps copied back into pinned host memory inside the timed region
   roofline     : the dominant kernel timed alone, algorithmic bytes / duration vs measured HBM peak
-  cpu_baseline : the reference's own CPU code (oracle/_ref) on the host cores, bounded sample
-  --impl reference : that CPU arm alone, same metric
+  nvlink       : (N > 1) the transposes fused into the FFT z passes: bytes pushed to peers / z-pass time vs 900 GB/s
+  parity       : (N > 1) a 128^3 slab-decomposed run against the same run on one GPU, done before timing
+  strong_scaling : the 1024^3 / nside 512 / 150 shells problem timed at this N (fixed problem for the 1-2-4-8 curve)
+  cpu_baseline : the reference's own CPU code (oracle/_ref) on the host cores (N = 1: the same 512^3 configuration)
+  --impl reference : that CPU arm alone, same metric and config; each step is the 512^3 sample of the workload
 """
 from __future__ import annotations
 
@@ -46,7 +49,7 @@ def load_tables(n_nu: int) -> dict:
     return t
 
 
-def t_total_c_host(n_grid: int, n_side: int, n_nu: int) -> dict:
+def t_total_c_host(n_grid: int, n_side: int, n_nu: int, n_gpus: int = 1) -> dict:
     """T_total as the reference's own total timer brackets it (main_gh.c:42,69) -- `./GetHI file` from
     param read through cosmology tables, device bring-up and the hot path to the last FITS map on disk (tmpfs),
     with this repository's C host (host/GetHI): the maps are written while they are still being downloaded."""
@@ -67,14 +70,22 @@ def t_total_c_host(n_grid: int, n_side: int, n_nu: int) -> dict:
             f"w= -1.0\nns= 0.96\nsigma_8= 0.8\nr_smooth= 2.0\nfrequencies_filename= {d}/nu.txt\nn_side= {n_side}\n"
             f"n_grid= {n_grid}\nseed= 1001\ndo_psources= 0\n")
         t0 = time.perf_counter()
-        r = subprocess.run([str(exe), str(d / "p.ini")], capture_output=True, text=True, timeout=600)
+        env = dict(os.environ)
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "GH_RANK", "GH_NRANKS"):  # the C host launches its own ranks
+            env.pop(k, None)
+        env["GH_HOST_TIMING"] = "1"
+        if n_gpus > 1:
+            env["GH_NGPUS"] = str(n_gpus)
+        r = subprocess.run([str(exe), str(d / "p.ini")], capture_output=True, text=True, timeout=600, env=env)
         wall = time.perf_counter() - t0
         if r.returncode != 0:
             return {"error": (r.stdout + r.stderr)[-300:]}
         m = re.search(r"Total time ellapsed ([0-9.]+) ms", r.stdout)
         written = sum(f.stat().st_size for f in d.glob("map_*.fits"))
         inside = float(m.group(1)) / 1e3 if m else None
-        return {"process_wall_s": round(wall, 3), "reference_total_timer_s": inside, "fits_bytes_written": written,
+        phases = {m_.group(1): float(m_.group(2)) for m_ in re.finditer(r"\[gh_host\] (.+?) ([0-9.]+) ms", r.stderr)}
+        return {"process_wall_s": round(wall, 3), "reference_total_timer_s": inside, "fits_bytes_written": written, "n_gpus": n_gpus,
+                "host_phase_ms": phases,
                 "mcells_per_s": (float(n_grid) ** 3 / inside / 1e6) if inside else None,
                 "what": "host/GetHI param file -> FITS maps on tmpfs: param read, cosmology tables, device bring-up, hot path, "
                         f"{n_nu} maps written by the streaming writer"}
@@ -179,7 +190,7 @@ def cpu_reference_run(n_grid: int, n_side: int, n_nu: int, steps: int, warmup: i
     except OSError:
         pass
     cells = float(n_grid) ** 3
-    times = []
+    times, stage = [], []
     if Reference.available():
         kind = "reference"
         ref = Reference()
@@ -192,14 +203,19 @@ def cpu_reference_run(n_grid: int, n_side: int, n_nu: int, steps: int, warmup: i
         os.dup2(devnull, 1)  # the reference prints its banner and timers on stdout
         try:
             par = ref.read_run_params(f"{tmp}/p.ini")
+            maps = ref.grid(par, "maps_HI", (n_nu, 12 * n_side * n_side))   # allocated once by the reference's reader
             for i in range(warmup + steps):
+                maps[:] = 0                                                 # outside the timed region
                 t0 = time.perf_counter()
                 ref.lib.ref_create_d_and_vr_fields(par)
+                t1 = time.perf_counter()
                 ref.lib.ref_get_HI(par)
-                ref.grid(par, "maps_HI", (n_nu, 12 * n_side * n_side))[:] = 0
+                t2 = time.perf_counter()
                 ref.lib.ref_mk_T_maps(par)
+                t3 = time.perf_counter()
                 if i >= warmup:
-                    times.append(time.perf_counter() - t0)
+                    times.append(t3 - t0)
+                    stage.append((t1 - t0, t2 - t1, t3 - t2))
         finally:
             os.dup2(saved, 1)
             os.close(devnull)
@@ -214,9 +230,32 @@ def cpu_reference_run(n_grid: int, n_side: int, n_nu: int, steps: int, warmup: i
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     t = float(np.mean(times))
+    st = np.mean(np.asarray(stage), axis=0) if stage else None
     return {"value": cells / t / 1e6, "unit": "Mcells/s", "cores": cores, "kind": kind, "seconds_per_step": t,
+            "stage_seconds": None if st is None else {"create_d_and_vr_fields": float(st[0]), "get_HI": float(st[1]), "mk_T_maps": float(st[2])},
             "sample": f"{n_grid}^3 grid, nside {n_side}, {n_nu} shells, {len(times)} step(s); FFT stage runs the oracle's "
                       f"own C FFT (FFTW is not installed), every other stage is the reference's code"}
+
+
+METRIC = "GetHI Mcells/s end-to-end"
+PK_NOTE = ("data/Pk_synth.dat: a synthetic CAMB-like linear P(k) (data/make_synthetic_pk.py) standing in for the reference's "
+           "data/Pk_CAMB_test.dat, which is not redistributed here; both arms read the same file")
+
+
+def make_config(n_grid: int, n_side: int, n_nu: int, world: int) -> dict:
+    """The `config` object: identical in both arms so that the driver compares like with like."""
+    cells = float(n_grid) ** 3
+    return {"workload": f"GetHI {n_grid}^3 grid, nside={n_side}, {n_nu} shells", "n_grid": n_grid, "n_side": n_side,
+            "n_nu": n_nu, "slabs": world, "cells_per_gpu": cells / world, "pk_file": PK_NOTE,
+            "l2": "inputs larger than L2: three %.2f GiB grids per GPU are swept every step" % (cells / world * 4 * (1 + 2.0 / n_grid) / 2**30)}
+
+
+def cpu_sample_of(n_grid: int, n_side: int, n_nu: int, cpu_grid: int = 0):
+    """The bounded sample the CPU arm times: the workload itself up to 512^3; larger grids are sampled at 512^3 with
+    n_side scaled by the same factor (same cells per pixel, same sub-particles per pixel) and the same shells."""
+    sg = cpu_grid or min(n_grid, 512)
+    ns = max(1, (n_side * sg) // n_grid) if sg < n_grid else n_side
+    return sg, ns, n_nu
 
 
 def run_reference_arm(args, workload):
@@ -224,18 +263,21 @@ def run_reference_arm(args, workload):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sg = args.cpu_grid or min(n_grid, 256)
-    steps = max(1, min(args.steps, 3))
-    r = cpu_reference_run(sg, n_side, n_nu, steps, min(args.warmup, 1))
+    sg, ns, nn = cpu_sample_of(n_grid, n_side, n_nu, args.cpu_grid)
+    r = cpu_reference_run(sg, ns, nn, args.steps, args.warmup)
+    whole = (sg, ns, nn) == (n_grid, n_side, n_nu)
     line = {
-        "impl": "reference", "metric": "GetHI Mcells/s end-to-end", "value": r["value"], "unit": "Mcells/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * r["seconds_per_step"],
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "Mcells/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 math, f32 storage",
         "data": "synthetic",
-        "config": {"workload": f"GetHI {n_grid}^3 grid, nside={n_side}, {n_nu} shells (timed on a bounded {sg}^3 sample)",
-                   "n_grid": n_grid, "n_side": n_side, "n_nu": n_nu, "sample_n_grid": sg},
+        "config": make_config(n_grid, n_side, n_nu, args.gpus),
+        "sample": {"n_grid": sg, "n_side": ns, "n_nu": nn, "whole_workload": whole,
+                   "what": "the workload itself" if whole else
+                   f"a {sg}^3 sample of the workload: n_side scaled with the grid ({ns}), same shells; Mcells/s of the sample"},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "stage_seconds": r.get("stage_seconds"),
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -251,10 +293,12 @@ def main():
     ap.add_argument("--grid", type=int, default=0)
     ap.add_argument("--nside", type=int, default=0)
     ap.add_argument("--shells", type=int, default=0)
-    ap.add_argument("--cpu-grid", type=int, default=0, help="grid of the bounded CPU sample (default min(grid,256))")
+    ap.add_argument("--cpu-grid", type=int, default=0, help="grid of the bounded CPU sample (default min(grid,512))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-t-total", action="store_true", help="skip the ./GetHI param-file-to-FITS run")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm (memory-capacity stress configs)")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the 128^3 decomposed-vs-single-GPU check before timing")
+    ap.add_argument("--no-strong", action="store_true", help="skip the fixed 1024^3 problem timed for the strong-scaling curve")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -300,22 +344,35 @@ def main():
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
+    # ---- parity before timing (N > 1): a 128^3 slab-decomposed run against the same run on one GPU --------------
+    parity = None
+    if world > 1 and not args.no_parity:
+        from crime_b200.selfcheck import decomposed_vs_single
+        pp = params_from_tables(load_tables(150), n_grid=128, n_side=64, seed=31337)
+        try:
+            parity = decomposed_vs_single(dist, pp, rank, world, local_rank, mode="full")
+        except Exception as exc:  # a failed check must show up in the line, not kill the measurement
+            parity = {"ok": False, "error": str(exc)[:300]} if rank == 0 else None
+        barrier()
+
+    if world > 1:
+        os.environ.setdefault("GH_TIME_FFT_PASSES", "1")  # events around the z passes: the NVLink figure below
     tables = load_tables(n_nu)
     params = params_from_tables(tables, n_grid=n_grid, n_side=n_side, seed=1001)
     g = GetHI(params, rank=rank, nranks=world, unique_id=uid, device=local_rank)
     stream = torch.cuda.ExternalStream(g.stream_handle(), device=dev)
     cells = float(n_grid) ** 3
 
-    def timed(fn, steps, finish=None):
+    def timed(gh, strm, fn, steps, finish=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
-        e0.record(stream)
+        e0.record(strm)
         for i in range(steps):
             fn(i)
         if finish is not None:
             finish()
-        e1.record(stream)
+        e1.record(strm)
         barrier()
         wall = time.perf_counter() - t0
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -338,7 +395,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = g.kernel_launches()
-    ms_res, _ = timed(step_resident, args.steps)
+    ms_res, _ = timed(g, stream, step_resident, args.steps)
     launches = g.kernel_launches() - l0
     if args.no_e2e:
         ms_e2e, wall_e2e = float("nan"), float("nan")
@@ -346,16 +403,27 @@ def main():
         for i in range(2):
             step_e2e(i)
         g.wait()
-        ms_e2e, wall_e2e = timed(step_e2e, args.steps, finish=g.wait)
+        ms_e2e, wall_e2e = timed(g, stream, step_e2e, args.steps, finish=g.wait)
         g.run(to_host=True)  # one synchronous realisation so that the per-stage timers below include an unoverlapped copy
     clocks = sampler.stop()
     stage_ms = g.stage_times()
+    z_pass = g.fft_pass_times() if world > 1 else None
 
-    # dominant kernel alone: every stage once more, each bracketed by its own events
-    g.generate_k(); g.fft_fields(); g.radial_velocity(); g.sigma_dens(); g.get_HI()
-    g.zero_maps(); g.synchronize()
-    g.accumulate_maps(); g.synchronize()
-    solo = g.stage_times()
+    # dominant kernel alone: every stage once more, each bracketed by its own events; on several ranks a barrier in
+    # front of each stage so that a stage's time is not somebody else's lateness
+    solo = {}
+    for name, call in (("kgen", g.generate_k), ("fft", g.fft_fields), ("vel", g.radial_velocity), ("sigma", g.sigma_dens),
+                       ("get_HI", g.get_HI), ("zero", g.zero_maps), ("maps", g.accumulate_maps)):
+        g.synchronize()
+        barrier()
+        call()
+        g.synchronize()
+        if name != "zero":
+            solo[name] = g.stage_times()[name]
+    if world > 1:  # the slowest rank's time of each stage
+        tt = torch.tensor([solo[k] for k in sorted(solo)], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        solo = dict(zip(sorted(solo), [float(v) for v in tt.tolist()]))
     nz_cells = cells / world
     bytes_per_cell = dict(STAGE_BYTES_PER_CELL)
     if world > 1:
@@ -370,17 +438,18 @@ def main():
     tf = ROOT / "profiles" / "roofline_traffic.json"
     if tf.exists():
         try:
-            traffic = json.loads(tf.read_text()).get(f"{top}:{n_grid}")
+            traffic = json.loads(tf.read_text()).get(f"{top}:{n_grid}" if world == 1 else f"{top}:{n_grid}:{world}")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": kernel_names[top], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_cell": bytes_per_cell[top], "ms": cand[top],
                 "stage_ms_alone": {k: round(v, 4) for k, v in solo.items()},
-                "stage_frac_of_hbm_peak": {k: round(bytes_per_cell[k] * nz_cells / (v * 1e-3) / 1e9 / peak, 4) for k, v in cand.items()}}
+                "stage_frac_of_hbm_peak": {k: round(bytes_per_cell[k] * nz_cells / (v * 1e-3) / 1e9 / peak, 4) for k, v in cand.items()},
+                "timed": "each stage alone after a stream synchronise" + (" and a cross-rank barrier; slowest rank" if world > 1 else "")}
     if top == "maps":
         n_sub = 10.0 * nz_cells
-        roofline["note"] = ("accumulate_kernel is bound by fp64 instruction and L2 atomic throughput, not HBM "
+        roofline["note"] = ("accumulate_kernel is bound by instruction issue and L2 atomic throughput, not HBM "
                             "(SURVEY 8d): also reporting sub-particles/s")
         roofline["subparticles_per_s"] = n_sub / (cand[top] * 1e-3)
 
@@ -393,18 +462,23 @@ def main():
         dist.all_gather(allt, tt)
         per_rank = [{k: round(float(v), 3) for k, v in zip(abi.STAGE_NAMES, a.tolist())} for a in allt]
     nvlink = None
-    if world > 1 and os.environ.get("GH_TIME_FFT_PASSES"):
-        # opt-in (GH_TIME_FFT_PASSES=1): the z passes carry the transposes; every rank pushes (P-1)/P of its slab of each
-        # field to its peers inside them.  Slowest rank's time, so the figure is the all-to-all's, not one link's.
-        zt = torch.tensor(list(g.fft_pass_times()), device=dev, dtype=torch.float64)
+    if world > 1:
+        # the z passes carry the transposes; every rank pushes (P-1)/P of its slab of each field to its peers inside
+        # them.  Slowest rank's time, so the figure is the all-to-all's, not one link's.
+        zt = torch.tensor(list(z_pass), device=dev, dtype=torch.float64)
         dist.all_reduce(zt, op=dist.ReduceOp.MAX)
         z_ms = [float(v) for v in zt.tolist()]
+        sent = (world - 1) / world * (cells / world) * (1 + 2.0 / n_grid) * 4.0   # bytes per rank per field
         if min(z_ms) > 0:
-            sent = (world - 1) / world * (cells / world) * (1 + 2.0 / n_grid) * 4.0   # bytes per rank per field
             ach = 2 * sent / (sum(z_ms) * 1e-3) / 1e9
             nvlink = {"achieved": ach, "peak": 900.0, "unit": "GB/s per GPU per direction", "frac": ach / 900.0,
                       "z_pass_ms": z_ms, "bytes_sent_per_rank_per_field": sent,
-                      "what": "transpose fused into the FFT z pass (peer stores), incl. the closing barrier; peak = NVLink 5 nominal"}
+                      "what": "transpose fused into the FFT z pass (peer stores over NVLink while the pass computes), incl. the "
+                              "barrier that closes it, last e2e step; the pass also reads and transforms the slab, so this is a "
+                              "lower bound on the link rate; peak = NVLink 5 nominal"}
+        else:
+            nvlink = {"achieved": None, "peak": 900.0, "unit": "GB/s per GPU per direction", "frac": None, "z_pass_ms": z_ms,
+                      "what": "z-pass timers unavailable"}
     n_here = g.n_shells_here
     table_bytes = sum(np.asarray(v).nbytes for k, v in tables.items() if k in abi.TABLE_FIELDS)
     maps_bytes = n_here * g.npix * 4
@@ -412,16 +486,58 @@ def main():
         mb = torch.tensor([float(maps_bytes), float(table_bytes)], device=dev, dtype=torch.float64)
         dist.all_reduce(mb)
         maps_bytes, table_bytes = int(mb[0].item()), int(mb[1].item())
+    g.end_fftw()
 
+    # ---- fixed problem for the strong-scaling curve: 1024^3 / nside 512 / 150 shells at this N ------------------------
+    strong = None
+    SS = (1024, 512, 150)
+    if not args.no_strong:
+        if (n_grid, n_side, n_nu) == SS:
+            strong = {"workload": "GetHI 1024^3 grid, nside=512, 150 shells", "ms_per_step": ms_res / args.steps,
+                      "value": cells * args.steps / (ms_res * 1e-3) / 1e6, "e2e_value": cells * args.steps / (ms_e2e * 1e-3) / 1e6,
+                      "steps": args.steps, "note": "this N's main workload"}
+        else:
+            try:
+                uid2 = None
+                if world > 1:
+                    from crime_b200.selfcheck import make_unique_id
+                    uid2 = make_unique_id(dist, rank)
+                ps = params_from_tables(load_tables(SS[2]), n_grid=SS[0], n_side=SS[1], seed=1001)
+                gs = GetHI(ps, rank=rank, nranks=world, unique_id=uid2, device=local_rank)
+                ss_stream = torch.cuda.ExternalStream(gs.stream_handle(), device=dev)
+                k = max(3, min(args.steps, 5))
+                for _ in range(3):
+                    gs.run(to_host=False)
+                ms_s, _ = timed(gs, ss_stream, lambda i: gs.run(to_host=False), k)
+
+                def ss_e2e(i):
+                    gs.set_params(ps)
+                    gs.run_async(i & 1)
+                for i in range(2):
+                    ss_e2e(i)
+                gs.wait()
+                ms_se, _ = timed(gs, ss_stream, ss_e2e, k, finish=gs.wait)
+                gs.end_fftw()
+                c3 = float(SS[0]) ** 3
+                strong = {"workload": "GetHI 1024^3 grid, nside=512, 150 shells", "ms_per_step": ms_s / k, "value": c3 * k / (ms_s * 1e-3) / 1e6,
+                          "e2e_value": c3 * k / (ms_se * 1e-3) / 1e6, "steps": k, "note": "timed after the main workload, same process"}
+            except Exception as exc:
+                strong = {"error": str(exc)[:300]}
+
+    if world > 1:
+        # the other ranks leave now (releasing their GPUs): what follows on rank 0 -- the C host's own multi-GPU run for
+        # T_total -- must not share the devices with ranks spinning in a barrier
+        dist.barrier(device_ids=[local_rank])
+        dist.destroy_process_group()
     if rank == 0:
         line = {
-            "metric": "GetHI Mcells/s end-to-end", "value": cells * args.steps / (ms_res * 1e-3) / 1e6, "unit": "Mcells/s",
+            "metric": METRIC, "value": cells * args.steps / (ms_res * 1e-3) / 1e6, "unit": "Mcells/s",
+            "value_definition": "device-resident: cells / CUDA-event time, parameters on the device, maps left there; "
+                                "`e2e` is the end-to-end figure (host tables in, host maps out, every step) and the headline",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 fields, f64 index arithmetic",
             "data": "synthetic",
-            "config": {"workload": f"GetHI {n_grid}^3 grid, nside={n_side}, {n_nu} shells", "n_grid": n_grid, "n_side": n_side,
-                       "n_nu": n_nu, "slabs": world, "cells_per_gpu": nz_cells,
-                       "l2": "inputs larger than L2: three %.2f GiB grids per GPU are swept every step" % (cells / world * 4 * (1 + 2.0 / n_grid) / 2**30)},
+            "config": make_config(n_grid, n_side, n_nu, world),
             "e2e": ({"value": None, "unit": "Mcells/s", "h2d_bytes_per_step": table_bytes, "d2h_bytes_per_step": maps_bytes,
                      "note": "--no-e2e"} if args.no_e2e else
                     {"value": cells * args.steps / (ms_e2e * 1e-3) / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": table_bytes,
@@ -436,25 +552,24 @@ def main():
             line["stage_ms_by_rank"] = per_rank
         if nvlink is not None:
             line["nvlink"] = nvlink
+        if parity is not None:
+            line["parity"] = parity
+        if strong is not None:
+            line["strong_scaling"] = strong
         if not args.no_cpu_baseline and world == 1:
-            sg = args.cpu_grid or min(n_grid, 256)
+            sg, ns, nn = cpu_sample_of(n_grid, n_side, n_nu, args.cpu_grid)
             try:
-                cb = cpu_reference_run(sg, n_side, n_nu, 1, 0)
+                cb = cpu_reference_run(sg, ns, nn, 2, 1)
                 line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
             except Exception as exc:  # the CPU arm must never take the GPU line down with it
                 line["cpu_baseline"] = {"value": None, "unit": "Mcells/s", "cores": os.cpu_count(), "kind": "port",
                                         "sample": f"failed: {exc}"}
-    g.end_fftw()
-    if rank == 0:
-        if world == 1 and not args.no_t_total:
+        if not args.no_t_total:
             try:
-                line["t_total"] = t_total_c_host(n_grid, n_side, n_nu)
+                line["t_total"] = t_total_c_host(n_grid, n_side, n_nu, world)
             except Exception as exc:
                 line["t_total"] = {"error": str(exc)}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier(device_ids=[local_rank])
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -141,6 +141,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         "gh_cuda_download_grid": ([vp, i32, vp], i32),
         "gh_cuda_upload_grid": ([vp, i32, vp], i32),
         "gh_cuda_set_sigma2_gauss": ([vp, C.c_double], i32),
+        "gh_cuda_grid_checksum": ([vp, i32, i32, i32, C.POINTER(u64)], i32),
         "gh_cuda_download_maps": ([vp, vp, u64, u64], i32),
         "gh_cuda_zero_maps": ([vp], i32),
         "gh_cuda_subparticle_offsets": ([vp, f64p], i32),
@@ -168,7 +169,7 @@ EXPORTED_SYMBOLS = (
     "gh_cuda_host_alloc", "gh_cuda_host_free", "gh_cuda_generate_k", "gh_cuda_fft_fields",
     "gh_cuda_radial_velocity", "gh_cuda_sigma_dens", "gh_cuda_accumulate_maps", "gh_cuda_synchronize",
     "gh_cuda_set_delta_k", "gh_cuda_clear_delta_k", "gh_cuda_download_delta_k", "gh_cuda_download_grid",
-    "gh_cuda_upload_grid", "gh_cuda_set_sigma2_gauss", "gh_cuda_download_maps", "gh_cuda_zero_maps",
+    "gh_cuda_upload_grid", "gh_cuda_set_sigma2_gauss", "gh_cuda_grid_checksum", "gh_cuda_download_maps", "gh_cuda_zero_maps",
     "gh_cuda_subparticle_offsets", "gh_cuda_points_to_shell_pixel", "gh_cuda_fastpath_audit", "gh_cuda_accumulate_audit", "gh_cuda_stage_times",
     "gh_cuda_kernel_launches", "gh_cuda_stream", "gh_cuda_last_error", "gh_cuda_version",
 )

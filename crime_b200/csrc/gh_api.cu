@@ -691,6 +691,7 @@ extern "C" int gh_cuda_host_free(void *ptr)
 extern "C" int gh_cuda_generate_k(gh_cuda_ctx *c)
 {
   GH_CTX(c);
+  c->sigma_ready = false;  // a new realisation: the measured variance no longer describes the density grid
   StageTimer t(c, GH_T_KGEN);
   return gh_launch_kgen(c);
 }
@@ -699,6 +700,7 @@ extern "C" int gh_cuda_fft_fields(gh_cuda_ctx *c)
 {
   GH_CTX(c);
   c->fft_stats_blocks = 0;
+  c->sigma_ready = false;
   StageTimer t(c, GH_T_FFT);
   if (gh_launch_fft_field(c, c->gridA)) return 1;  // src/fourier.c:391
   return gh_launch_fft_field(c, c->gridB);         // src/fourier.c:392
@@ -748,7 +750,8 @@ extern "C" int gh_cuda_get_HI(gh_cuda_ctx *c)
 {
   GH_CTX(c);
   c->fft_stats_blocks = 0;  // the density grid turns into HI mass
-  GH_REQUIRE(c->sigma_ready, "gh_cuda_get_HI: sigma2_gauss not set (run create_d_and_vr_fields or set it)");
+  GH_REQUIRE(c->sigma_ready || c->sigma_overridden,
+             "gh_cuda_get_HI: sigma2_gauss not known for this density grid (run gh_cuda_sigma_dens / create_d_and_vr_fields, or set it)");
   StageTimer t(c, GH_T_GETHI);
   return gh_launch_get_HI(c);
 }
@@ -992,6 +995,7 @@ extern "C" int gh_cuda_set_delta_k(gh_cuda_ctx *c, const float *dens_k, const fl
   GH_CUDA_OK(cudaMemcpy2DAsync(c->gridB, width, vpot_k + off, spitch, width, d.n, cudaMemcpyHostToDevice, c->stream));
   GH_CUDA_OK(cudaStreamSynchronize(c->stream));
   c->k_injected = true;
+  c->sigma_ready = false;
   return 0;
 }
 
@@ -1029,8 +1033,25 @@ extern "C" int gh_cuda_upload_grid(gh_cuda_ctx *c, int which, const float *slab_
   GH_CTX(c);
   float2 *g = grid_ptr(c, which);
   GH_REQUIRE(g && slab_in, "gh_cuda_upload_grid: bad grid id %d or null input", which);
-  if (which == GH_GRID_DENS) c->fft_stats_blocks = 0;  // the FFT's partial sums no longer describe this grid
+  if (which == GH_GRID_DENS) { c->fft_stats_blocks = 0; c->sigma_ready = false; }  // the FFT's sums / the variance no longer describe this grid
   GH_CUDA_OK(cudaMemcpyAsync(g, slab_in, c->slab_complex * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+  GH_CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int gh_cuda_grid_checksum(gh_cuda_ctx *c, int which, int z0_local, int n_planes, unsigned long long *sum_out)
+{
+  GH_CTX(c);
+  float2 *g = grid_ptr(c, which);
+  GH_REQUIRE(g && sum_out, "gh_cuda_grid_checksum: bad grid id %d or null output", which);
+  GH_REQUIRE(z0_local >= 0 && n_planes >= 0 && z0_local + n_planes <= c->d.nz_here, "gh_cuda_grid_checksum: planes [%d,%d) outside the slab",
+             z0_local, z0_local + n_planes);
+  *sum_out = 0ULL;
+  if (n_planes == 0) return 0;
+  unsigned long long *d_sum = reinterpret_cast<unsigned long long *>(c->d_partials + 7);  // a slot no kernel of the path uses
+  GH_CUDA_OK(cudaMemsetAsync(d_sum, 0, sizeof(*d_sum), c->stream));
+  if (gh_launch_checksum(c, reinterpret_cast<const float *>(g), z0_local, n_planes, d_sum)) return 1;
+  GH_CUDA_OK(cudaMemcpyAsync(sum_out, d_sum, sizeof(*d_sum), cudaMemcpyDeviceToHost, c->stream));
   GH_CUDA_OK(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -1039,10 +1060,9 @@ extern "C" int gh_cuda_set_sigma2_gauss(gh_cuda_ctx *c, double sigma2)
 {
   GH_REQUIRE(c, "null gh_cuda context");
   c->sigma2_gauss = sigma2;
-  c->sigma_overridden = true;
-  c->sigma_ready = true;
+  c->sigma_overridden = true;  // get_HI reads d_partials[6] from now on (until gh_cuda_set_params)
   GH_CUDA_OK(cudaSetDevice(c->device));
-  GH_CUDA_OK(cudaMemcpyAsync(c->d_partials + 5, &c->sigma2_gauss, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  GH_CUDA_OK(cudaMemcpyAsync(c->d_partials + 6, &c->sigma2_gauss, sizeof(double), cudaMemcpyHostToDevice, c->stream));
   GH_CUDA_OK(cudaStreamSynchronize(c->stream));
   return 0;
 }

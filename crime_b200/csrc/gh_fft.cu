@@ -260,7 +260,7 @@ __device__ __forceinline__ void rows_passes(float2 *sm, const float2 *__restrict
   }
 }
 
-// STATS: also leave this CTA's sum and sum of squares of the real cells it produced in stats[2 + 2*blockIdx.x ..]
+// STATS: also leave this CTA's sum and sum of squares of the real cells it produced in stats[GH_PARTIALS_BASE + 2*blockIdx.x ..]
 // (float product, double accumulation, fixed order: compute_sigma_dens, src/fourier.c:24-76, without re-reading
 // the density field).
 template <int N, int W, int NT, bool STATS>
@@ -327,8 +327,8 @@ __global__ void __launch_bounds__(NT) fft_c2r_rows_kernel(float2 *__restrict__ d
       double a = 0.0, b = 0.0;
 #pragma unroll
       for (int i = 0; i < NT / 32; ++i) { a += red[0][i]; b += red[1][i]; }
-      stats[2 + 2 * (size_t)blockIdx.x] = a;
-      stats[3 + 2 * (size_t)blockIdx.x] = b;
+      stats[GH_PARTIALS_BASE + 2 * (size_t)blockIdx.x] = a;
+      stats[GH_PARTIALS_BASE + 1 + 2 * (size_t)blockIdx.x] = b;
     }
   }
 }

@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(256) sigma_partial_kernel(GhDev d, const float
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    partials[2 + 2 * blockIdx.x] = sh1[0];
-    partials[3 + 2 * blockIdx.x] = sh2[0];
+    partials[GH_PARTIALS_BASE + 2 * blockIdx.x] = sh1[0];
+    partials[GH_PARTIALS_BASE + 1 + 2 * blockIdx.x] = sh2[0];
   }
 }
 
@@ -99,8 +99,8 @@ __global__ void __launch_bounds__(256) sigma_final_kernel(double *__restrict__ p
   __shared__ double sh1[256], sh2[256];
   double s1 = 0.0, s2 = 0.0;
   for (int i = threadIdx.x; i < nblocks; i += 256) {
-    s1 += partials[2 + 2 * i];
-    s2 += partials[3 + 2 * i];
+    s1 += partials[GH_PARTIALS_BASE + 2 * i];
+    s2 += partials[GH_PARTIALS_BASE + 1 + 2 * i];
   }
   sh1[threadIdx.x] = s1;
   sh2[threadIdx.x] = s2;
@@ -122,14 +122,13 @@ __global__ void __launch_bounds__(256) sigma_final_kernel(double *__restrict__ p
 // The four numbers the host wants (sum, sum of squares, mean, variance) are stored straight into mapped pinned
 // host memory: a cudaMemcpyAsync here would queue behind the previous realisation's 200 MB map download on the
 // device->host copy engine and stall the compute stream for ~1 ms (measured).  A caller-supplied sigma2_gauss
-// (gh_cuda_set_sigma2_gauss) replaces the measured variance for get_HI.
-__global__ void sigma_finish_kernel(double *__restrict__ partials, double inv_ng_tot, double *__restrict__ host_stats,
-                                    int overridden, double sigma2_override)
+// (gh_cuda_set_sigma2_gauss) lives in its own slot, partials[6], which nothing here writes.
+__global__ void sigma_finish_kernel(double *__restrict__ partials, double inv_ng_tot, double *__restrict__ host_stats)
 {
   const double sum = partials[0], sumsq = partials[1];
   const double mean = sum * inv_ng_tot, var = sumsq * inv_ng_tot - mean * mean;
   partials[4] = mean;
-  partials[5] = overridden ? sigma2_override : var;
+  partials[5] = var;
   host_stats[0] = sum; host_stats[1] = sumsq; host_stats[2] = mean; host_stats[3] = var;
   __threadfence_system();
 }
@@ -139,9 +138,9 @@ __global__ void sigma_finish_kernel(double *__restrict__ partials, double inv_ng
 // bias_HI / fraction_HI (src/user_defined.c:27-35), in place: dens <- HI mass, rvel <- Delta z_RSD.
 // 8 B read + 8 B written per cell; the three 5001-entry float tables are read through L1.
 __global__ void __launch_bounds__(256) get_HI_kernel(GhDev d, Axes3 axes, float *__restrict__ dens, float *__restrict__ rvel,
-                                                     const double *__restrict__ sigma_stats)
+                                                     const double *__restrict__ sigma2_ptr)
 {
-  const GetHIConsts k = make_gethi_consts(d, (float)sigma_stats[5]);  // the variance stays on the device
+  const GetHIConsts k = make_gethi_consts(d, (float)*sigma2_ptr);  // the variance stays on the device
   const int ngx = 2 * d.nh;
   const int iy = blockIdx.y, iz = blockIdx.z;
   const AxisF ax = axes.x;
@@ -170,9 +169,9 @@ __global__ void __launch_bounds__(256) get_HI_kernel(GhDev d, Axes3 axes, float 
 __global__ void __launch_bounds__(256) velocity_get_HI_kernel(GhDev d, Axes3 axes, const float *__restrict__ vpot,
                                                               const float *__restrict__ plane_lo,
                                                               const float *__restrict__ plane_hi, float *__restrict__ dens,
-                                                              float *__restrict__ dz_out, const double *__restrict__ sigma_stats)
+                                                              float *__restrict__ dz_out, const double *__restrict__ sigma2_ptr)
 {
-  const GetHIConsts k = make_gethi_consts(d, (float)sigma_stats[5]);
+  const GetHIConsts k = make_gethi_consts(d, (float)*sigma2_ptr);
   const int ngx = 2 * d.nh;
   const int iy = blockIdx.y, iz = blockIdx.z;
   const float hidx = d.half_inv_dx;
@@ -216,7 +215,39 @@ __global__ void __launch_bounds__(256) velocity_get_HI_kernel(GhDev d, Axes3 axe
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Position-weighted checksum of the real cells of a plane range: sum over cells of bits(value) * (2*g + 1) mod 2^64
+// with g the cell's global index (zg*n + iy)*n + ix.  Integer addition commutes, so the result does not depend on
+// the order of the atomics; two slab decompositions of a bit-identical field give identical per-plane-range sums
+// (tests: 2048^3 on eight GPUs against one GPU without moving 100 GB of grids through the host).
+__global__ void __launch_bounds__(256) checksum_kernel(const uint32_t *__restrict__ grid, int n, int ngx, int nplanes,
+                                                       long long zg0, unsigned long long *__restrict__ out)
+{
+  const long long nrows = (long long)nplanes * n;
+  unsigned long long acc = 0ULL;
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const unsigned long long g0 = (unsigned long long)((zg0 + row / n) * n + row % n) * (unsigned long long)n;
+    const uint32_t *r = grid + row * ngx;
+    for (int ix = threadIdx.x; ix < n; ix += blockDim.x) acc += (unsigned long long)__ldg(r + ix) * (2ULL * (g0 + ix) + 1ULL);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
 }  // namespace
+
+int gh_launch_checksum(gh_cuda_ctx *c, const float *grid, int z0_local, int nplanes, unsigned long long *d_out)
+{
+  const GhDev &d = c->d;
+  const int ngx = 2 * d.nh;
+  long long blocks = (long long)nplanes * d.n;
+  if (blocks > c->n_sm * 16) blocks = c->n_sm * 16;
+  checksum_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t *>(grid) + (size_t)z0_local * d.n * ngx, d.n, ngx,
+                                                           nplanes, (long long)d.iz0 + z0_local, d_out);
+  GH_LAUNCH_CHECK(c);
+  return 0;
+}
 
 // neighbour planes of the velocity potential for this slab's first and last plane
 static int halo_planes(gh_cuda_ctx *c, const float **lo_out, const float **hi_out)
@@ -262,7 +293,7 @@ int gh_launch_velocity_get_HI(gh_cuda_ctx *c)
   dim3 grid((d.n / 2 + 255) / 256, d.n, d.nz_here);
   const Axes3 axes = {make_axis(d.dx, d.pos_obs[0], 0), make_axis(d.dx, d.pos_obs[1], 0), make_axis(d.dx, d.pos_obs[2], d.iz0)};
   velocity_get_HI_kernel<<<grid, 256, 0, c->stream>>>(d, axes, vpot, lo, hi, reinterpret_cast<float *>(c->gridA),
-                                                      reinterpret_cast<float *>(c->gridC), c->d_partials);
+                                                      reinterpret_cast<float *>(c->gridC), c->d_partials + (c->sigma_overridden ? 6 : 5));
   GH_LAUNCH_CHECK(c);
   return 0;
 }
@@ -302,7 +333,7 @@ int gh_launch_sigma(gh_cuda_ctx *c)
 int gh_launch_sigma_finish(gh_cuda_ctx *c)
 {
   const double ng_tot = (double)c->d.n * ((double)c->d.n * (double)c->d.n);
-  sigma_finish_kernel<<<1, 1, 0, c->stream>>>(c->d_partials, 1.0 / ng_tot, c->h_stats_dev, c->sigma_overridden ? 1 : 0, c->sigma2_gauss);
+  sigma_finish_kernel<<<1, 1, 0, c->stream>>>(c->d_partials, 1.0 / ng_tot, c->h_stats_dev);
   GH_LAUNCH_CHECK(c);
   return 0;
 }
@@ -313,7 +344,7 @@ int gh_launch_get_HI(gh_cuda_ctx *c)
   dim3 grid((d.n / 2 + 255) / 256, d.n, d.nz_here);
   const Axes3 axes = {make_axis(d.dx, d.pos_obs[0], 0), make_axis(d.dx, d.pos_obs[1], 0), make_axis(d.dx, d.pos_obs[2], d.iz0)};
   get_HI_kernel<<<grid, 256, 0, c->stream>>>(d, axes, reinterpret_cast<float *>(c->gridA), reinterpret_cast<float *>(c->gridC),
-                                             c->d_partials);
+                                             c->d_partials + (c->sigma_overridden ? 6 : 5));
   GH_LAUNCH_CHECK(c);
   return 0;
 }

@@ -45,6 +45,11 @@ struct GhDev {
   float sub_mono[8 * GH_CUDA_N_SUBPART];
 };
 
+// d_partials layout (doubles): [0..1] sum, sum of squares (all-reduced); [4] mean; [5] measured variance;
+// [6] caller-supplied variance (gh_cuda_set_sigma2_gauss); per-CTA partial sums start at GH_PARTIALS_BASE, so no
+// partial-sum kernel ever touches the slots get_HI reads
+#define GH_PARTIALS_BASE 8
+
 #define GH_MAX_RANKS 16
 #define GH_MAX_CHUNKS 64
 
@@ -145,9 +150,10 @@ int gh_launch_fft_field(gh_cuda_ctx *c, float2 *field);  // full c2r of one fiel
 int gh_fft_supported(int n);
 int gh_launch_radial_velocity(gh_cuda_ctx *c);
 int gh_launch_sigma(gh_cuda_ctx *c);  // leaves (sum, sumsq) in c->d_partials[0..1]
-int gh_launch_sigma_finish(gh_cuda_ctx *c);  // d_partials[4] = mean, [5] = sigma2_gauss
+int gh_launch_sigma_finish(gh_cuda_ctx *c);  // d_partials[4] = mean, [5] = measured sigma2_gauss
 int gh_launch_get_HI(gh_cuda_ctx *c);
 int gh_launch_halo_exchange(gh_cuda_ctx *c);
+int gh_launch_checksum(gh_cuda_ctx *c, const float *grid, int z0_local, int nplanes, unsigned long long *d_out);
 int gh_launch_velocity_get_HI(gh_cuda_ctx *c);
 int gh_launch_accumulate(gh_cuda_ctx *c, const float *mass, const float *dzrsd, int iz_base, int zg_base, int nplanes);
 int gh_stream_barrier(gh_cuda_ctx *c);  // every rank has reached this point of its stream

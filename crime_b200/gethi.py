@@ -213,6 +213,13 @@ class GetHI:
         self._check(self.lib.gh_cuda_set_sigma2_gauss(self._ctx, float(s2)))
         self.sigma2_gauss = float(s2)
 
+    def grid_checksum(self, which: int, z0_local: int = 0, n_planes: int | None = None) -> int:
+        """Position-weighted checksum of the real cells of planes [z0_local, z0_local+n_planes) of this slab."""
+        out = C.c_ulonglong()
+        n_planes = self.nz_here - z0_local if n_planes is None else n_planes
+        self._check(self.lib.gh_cuda_grid_checksum(self._ctx, which, z0_local, n_planes, C.byref(out)))
+        return int(out.value)
+
     def download_maps(self) -> np.ndarray:
         """Full per-rank stack as it sits on the device before any cross-rank reduction."""
         out = np.zeros((self.params.n_nu, self.npix), np.float32)

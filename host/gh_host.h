@@ -58,13 +58,15 @@ typedef struct ParamGetHI {
   gh_cuda_ctx *cuda;
 } ParamGetHI;
 
-/* process bring-up: src/common_gh.c:31 (mpi_init).  Rank / size / NCCL id come from the launcher:
- * GH_RANK, GH_NRANKS (or RANK / WORLD_SIZE / LOCAL_RANK), id passed through gh_set_unique_id */
+/* process bring-up: src/common_gh.c:31 (mpi_init).  Rank / size / NCCL id come from the launcher (host/main.c):
+ * GH_NGPUS=P forks P ranks and pipes the id; or GH_RANK, GH_NRANKS (or RANK / WORLD_SIZE / LOCAL_RANK) with the id
+ * in the file GH_UNIQUE_ID_FILE */
 extern int NodeThis, NNodes;
 void gh_mpi_init(int rank, int nranks, int device, const void *unique_id);
 void print_info(const char *fmt, ...);
 void report_error(int level, const char *fmt, ...);
 void timer(int i);
+void gh_phase(const char *name); /* GH_HOST_TIMING=1: time since the previous call, labelled, on stderr */
 
 /* src/io_gh.c */
 ParamGetHI *read_run_params(const char *fname);

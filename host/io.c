@@ -101,8 +101,11 @@ ParamGetHI *read_run_params_ex(const char *fname, int with_device)
   if (have_nutable) read_nutable(par);
   else { par->nu_min = nu_min_key; par->nu_max = nu_max_key; par->n_nu = n_nu_key; }
   if (par->do_psources) report_error(1, "do_psources=1 is not part of the GPU hot path (the reference README discourages it)\n");
+  gh_phase("parameter file");
   cosmo_set(par);
+  gh_phase("cosmo_set");
   if (with_device) init_fftw(par);
+  gh_phase("init_fftw (CUDA context, device and pinned allocations, NCCL)");
 
   const double dk = 2 * M_PI / par->l_box;
   const double dtheta = sqrt(41253. / (12 * par->n_side * par->n_side));

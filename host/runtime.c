@@ -54,6 +54,17 @@ static double now_s(void)
   return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
 
+/* GH_HOST_TIMING=1: wall time of each host phase on stderr (rank 0), for the T_total breakdown of bench.py */
+void gh_phase(const char *name)
+{
+  static double last = 0;
+  static int on = -1;
+  if (on < 0) on = getenv("GH_HOST_TIMING") != NULL;
+  const double t = now_s();
+  if (on && NodeThis == 0 && name && last > 0) fprintf(stderr, "[gh_host] %s %.1f ms\n", name, 1000 * (t - last));
+  last = t;
+}
+
 void timer(int i)
 {
   static double rel0, abs0;

@@ -181,6 +181,11 @@ int gh_cuda_download_delta_k(gh_cuda_ctx *ctx, float *dens_k, float *vpot_k);
 int gh_cuda_download_grid(gh_cuda_ctx *ctx, int which, float *slab_out);
 int gh_cuda_upload_grid(gh_cuda_ctx *ctx, int which, const float *slab_in);
 int gh_cuda_set_sigma2_gauss(gh_cuda_ctx *ctx, double sigma2_gauss);
+/* Position-weighted checksum of the real cells of planes [z0_local, z0_local+n_planes) of this rank's slab:
+ * sum of bits(value) * (2*g + 1) mod 2^64, g = (z_global*N + y)*N + x.  Bit-identical fields give identical sums
+ * whatever the slab decomposition: lets a test compare a 2048^3 run on eight GPUs with one GPU's plane by plane
+ * without moving the grids (the reference has no counterpart; its fields are checked by eye). */
+int gh_cuda_grid_checksum(gh_cuda_ctx *ctx, int which, int z0_local, int n_planes, unsigned long long *sum_out);
 /* un-normalised or final map stack as it sits on this rank's device: [n_nu][npix] before the
  * reduction (full stack), use n_floats to bound the copy */
 int gh_cuda_download_maps(gh_cuda_ctx *ctx, float *maps_out, unsigned long long first, unsigned long long n_floats);

@@ -244,7 +244,17 @@ class Reference:
         lib.ref_set_fft_io.argtypes = [_vp, _vp, _vp, _vp]
 
     def read_run_params(self, fname: str):
-        return self.lib.ref_read_run_params(str(fname).encode())
+        """The reference's -D_DEBUG cosmo_set dumps test_cosmo.dat into the current directory: run it from a
+        scratch directory so that the working tree stays clean (paths in the parameter file must be absolute)."""
+        import tempfile
+        fname = str(Path(fname).resolve())
+        cwd = os.getcwd()
+        with tempfile.TemporaryDirectory() as scratch:
+            os.chdir(scratch)
+            try:
+                return self.lib.ref_read_run_params(fname.encode())
+            finally:
+                os.chdir(cwd)
 
     def get(self, par, name: str) -> float:
         return self.lib.ref_get_double(par, name.encode())

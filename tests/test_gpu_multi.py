@@ -34,10 +34,30 @@ def test_slab_decomposition_matches_single_gpu(world, n_grid, n_side, bounds):
         env["GH_SPARSE_REDUCE"] = "1"
     elif bounds:
         env["GH_MAP_BOUNDS"] = bounds
+    _run_worker(world, n_grid, n_side, "full", env, f"{world}gpu_{n_grid}_{bounds or 'model'}")
+
+
+def _run_worker(world, n_grid, n_side, mode, env, tag):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(29400 + world), str(ROOT / "tests" / "multi_gpu_worker.py"), str(n_grid), str(n_side)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+           "--master-port", str(29400 + world), str(ROOT / "tests" / "multi_gpu_worker.py"), str(n_grid), str(n_side), mode]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1500, env=env)
+    out = ROOT / "gpurun_out" / "multi_gpu"
+    out.mkdir(parents=True, exist_ok=True)
+    lines = [l for l in r.stdout.splitlines() if l.startswith(("MULTI_GPU_", "rank "))]
+    (out / f"{tag.replace(',', '_')}.log").write_text("\n".join(lines) + "\n")
     assert "MULTI_GPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("world,n_grid,n_side", [(2, 1024, 512), (4, 1024, 512), (8, 2048, 1024)])
+def test_benchmark_configurations_match_single_gpu(world, n_grid, n_side):
+    """The BASELINE.json multi-GPU configurations themselves (150 shells): per-slab checksums of all five grids and
+    the shell maps against the same run on one GPU (2048^3 needs 103 GiB on rank 0's device).  GH_TEST_LARGE=1."""
+    import os
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    if not os.environ.get("GH_TEST_LARGE"):
+        pytest.skip("large-grid multi-GPU check: GH_TEST_LARGE=1")
+    _run_worker(world, n_grid, n_side, "hash", dict(os.environ), f"{world}gpu_{n_grid}_hash")
 
 
 def test_c_host_fork_launcher_two_gpus(tmp_path):

@@ -215,16 +215,25 @@ def test_kgen_matches_oracle_philox(oracle, tables_nu64, n_grid):
     assert dk[0, 0, 0] == 0 and vk[0, 0, 0] == 0
 
 
-@pytest.mark.parametrize("n_grid,n_side,n_nu_tab", [(64, 32, "nu64"), (128, 64, "nu150")])
+@pytest.mark.parametrize("n_grid,n_side,n_nu_tab", [(64, 32, "nu64"), (128, 64, "nu150"), (512, 256, "nu64")])
 def test_whole_path_against_oracle(oracle, tables_nu64, tables_nu150, n_grid, n_side, n_nu_tab):
-    """Philox realisation -> maps, GPU vs oracle, every intermediate field."""
+    """Philox realisation -> maps, GPU vs oracle, every intermediate field.  The last case is the benchmark
+    configuration itself (BASELINE.json configs[1]: 512^3, nside 256, 64 shells; bench.py's seed): it exercises the
+    512-point FFT instantiations, the fused variance sums and the map kernel at the sizes bench.py times."""
     from crime_b200 import GetHI, params_from_tables
     from crime_b200.abi import GRID_DENS, GRID_RVEL, GRID_VPOT
     tabs = tables_nu64 if n_nu_tab == "nu64" else tables_nu150
-    p = params_from_tables(tabs, n_grid=n_grid, n_side=n_side, seed=4242)
+    p = params_from_tables(tabs, n_grid=n_grid, n_side=n_side, seed=1001 if n_grid == 512 else 4242)
     n = n_grid
     dk_o, vk_o = oracle.kgen_philox(p)
     with GetHI(p) as g:
+        # the device's own k-space realisation against the oracle's restatement of the same stream
+        g.generate_k()
+        dk, vk = g.download_delta_k()
+        m = np.abs(dk_o) > 0
+        assert (np.abs(dk - dk_o)[m] / np.abs(dk_o)[m]).max() < TOL
+        assert (np.abs(vk - vk_o)[m] / np.abs(vk_o)[m]).max() < TOL
+        del dk, vk, m
         # feed the oracle's k-space so that later stages are compared on identical input
         g.set_delta_k(dk_o, vk_o)
         s2 = g.create_d_and_vr_fields()
@@ -534,7 +543,6 @@ def test_experimental_taylor_pixelisation_audit(tables_nu64):
             assert a["unsure"] < 0.03 * (a["inside"] + a["unsure"]), a
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("GH_TEST_EXPERIMENTAL"), reason="linked after the round's GPU budget was spent; not yet run on hardware")
 def test_reference_own_driver_on_the_gpu_path(tmp_path):
     """oracle/_ref/GetHI_gpu: the reference's own driver, parameter reader, cosmology and FITS writer with its hot
     path replaced by libgh_cuda.so through the glue of INTEGRATION.md.  Its maps must equal what the Python
@@ -550,7 +558,7 @@ def test_reference_own_driver_on_the_gpu_path(tmp_path):
     write_nutable(tmp_path / "nu.txt", 10)
     write_param_file(tmp_path / "p.ini", n_grid=64, n_side=16, nutable=tmp_path / "nu.txt",
                      pk_file=root / "data" / "Pk_synth.dat", prefix=tmp_path / "drop", seed=21)
-    r = subprocess.run([str(exe), str(tmp_path / "p.ini")], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([str(exe), str(tmp_path / "p.ini")], capture_output=True, text=True, timeout=300, cwd=tmp_path)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     ref = Reference()
     p = ref.params(ref.read_run_params(tmp_path / "p.ini"))
@@ -564,8 +572,8 @@ def test_reference_own_driver_on_the_gpu_path(tmp_path):
             assert np.abs(m[nz] / maps[s][nz] - 1).max() < 1e-5
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("GH_TEST_LARGE"), reason="large-grid checks (tens of GB of host memory, minutes of CPU): GH_TEST_LARGE=1")
-@pytest.mark.parametrize("n", [512, 1024])
+@pytest.mark.parametrize("n", [512, pytest.param(1024, marks=pytest.mark.skipif(
+    not __import__("os").environ.get("GH_TEST_LARGE"), reason="1024^3 against pocketfft (20 GB of host memory): GH_TEST_LARGE=1"))])
 def test_fft_large_grids_against_pocketfft(tables_nu64, n):
     """The FFT kernels are instantiated per line length with their own tile widths and radix plans (512: W=16, 8*8*8;
     1024: W=8 strided / 16 rows, 8*8*4*4).  Whole-field comparison with scipy's float32 c2r (same semantics as the
@@ -608,3 +616,82 @@ def test_fft_2048_variance_against_the_input_spectrum(tables_nu150):
         expected += (np.where(k2 > 0, pkv / dk ** 3 * np.exp(-p.r2_smooth * k2), 0.0) * wgt).sum()
     expected *= (np.sqrt(2 * np.pi) / p.l_box) ** 6
     assert abs(s2 / expected - 1) < 0.01
+
+
+def test_grid_checksum_matches_numpy(tables_nu64):
+    """gh_cuda_grid_checksum (what the large multi-GPU parity test compares instead of moving 100 GB of grids):
+    sum of bits(value) * (2 g + 1) mod 2^64 over the real cells, g the global cell index."""
+    from crime_b200 import GetHI, params_from_tables
+    from crime_b200.abi import GRID_DENS, GRID_VPOT
+    n = 64
+    p = params_from_tables(tables_nu64, n_grid=n, n_side=16, seed=8)
+    with GetHI(p) as g:
+        g.create_d_and_vr_fields()
+        for which in (GRID_DENS, GRID_VPOT):
+            f = g.download_grid(which)[:, :, :n]
+            bits = np.ascontiguousarray(f).view(np.uint32).astype(np.uint64)
+            idx = np.arange(n ** 3, dtype=np.uint64).reshape(n, n, n)
+            with np.errstate(over="ignore"):
+                full = int((bits * (np.uint64(2) * idx + np.uint64(1))).sum(dtype=np.uint64))
+                part = int((bits[10:25] * (np.uint64(2) * idx[10:25] + np.uint64(1))).sum(dtype=np.uint64))
+            assert g.grid_checksum(which) == full
+            assert g.grid_checksum(which, 10, 15) == part
+        assert g.grid_checksum(GRID_DENS) != g.grid_checksum(GRID_VPOT)
+
+
+def test_caller_supplied_sigma2_survives_the_staged_calls(tables_nu64, oracle):
+    """A staged caller that supplies sigma2_gauss and then runs fft_fields / radial_velocity / get_HI without
+    gh_cuda_sigma_dens must get HI masses computed from ITS value (the variance slots are separate from the partial
+    sums the FFT leaves behind), and a caller that supplies nothing and skips sigma_dens must be refused."""
+    from crime_b200 import GetHI, GetHIError, params_from_tables
+    from crime_b200.abi import GRID_DENS, GRID_RVEL
+    n = 64
+    p = params_from_tables(tables_nu64, n_grid=n, n_side=16, seed=3)
+    with GetHI(p) as g:
+        g.generate_k(); g.fft_fields(); g.radial_velocity()
+        with pytest.raises(GetHIError):
+            g.get_HI()                                   # no variance known for this density grid
+        dens, rvel = g.download_grid(GRID_DENS), g.download_grid(GRID_RVEL)
+        s2_forced = 0.123
+        g.set_sigma2_gauss(s2_forced)
+        g.generate_k(); g.fft_fields(); g.radial_velocity()   # the density FFT rewrites its per-CTA partial sums
+        g.get_HI()
+        mass = g.download_grid(GRID_DENS)[:, :, :n]
+        ref_m, _ = oracle.get_HI(p, s2_forced, dens, rvel)
+        assert np.abs(mass / ref_m[:, :, :n] - 1).max() < TOL
+        # a fresh parameter block drops the override: the measured variance is used again
+        g.set_params(p)
+        s2 = g.create_d_and_vr_fields()
+        g.get_HI()
+        mass2 = g.download_grid(GRID_DENS)[:, :, :n]
+        ref_m2, _ = oracle.get_HI(p, s2, dens, rvel)
+        assert np.abs(mass2 / ref_m2[:, :, :n] - 1).max() < TOL
+
+
+@pytest.mark.parametrize("seed", range(1001, 1009))
+def test_statistical_acceptance_of_the_device_realisation(tables_nu64, seed):
+    """north_star / SURVEY 8(d): the GPU's own 256^3 output for the eight named seeds -- binned P(k) against
+    pk_linear0 * exp(-r_s^2 k^2), phase uniformity, one-point PDF of delta_G, <rho_LN> = 1 (tolerances stated in
+    tests/stat_checks.py).  Reference generator: src/fourier.c:285-299, src/common.c:154-164."""
+    import json, os
+    import stat_checks as sc
+    from crime_b200 import GetHI, params_from_tables
+    from crime_b200.abi import GRID_DENS
+    n = 256
+    p = params_from_tables(tables_nu64, n_grid=n, n_side=16, seed=seed)
+    with GetHI(p) as g:
+        g.generate_k()
+        dk, _ = g.download_delta_k()
+        s2 = g.create_d_and_vr_fields()
+        dens = g.download_grid(GRID_DENS)
+        g.get_HI()
+        mass = g.download_grid(GRID_DENS)
+        mean = g.mean_gauss
+    kr = sc.check_kspace(p, tables_nu64, dk)
+    one = sc.check_one_point(dens, s2, mean, n)
+    lm = sc.lognormal_mean(p, tables_nu64, mass, n)
+    os.makedirs("gpurun_out/stats", exist_ok=True)
+    with open(f"gpurun_out/stats/device_realisation_seed{seed}.json", "w") as f:
+        json.dump({"kspace": {k: (v if k != "zero_mode" else abs(v)) for k, v in kr.items()}, "one_point": one,
+                   "lognormal_mean": lm[0], "lognormal_mean_sigma": lm[1], "sigma2_gauss": s2}, f, indent=1)
+    sc.assert_acceptance(kr, one, *lm)

@@ -67,3 +67,45 @@ def test_fits_round_trip(tmp_path):
 def test_cli_usage_and_missing_gpu(tmp_path):
     r = subprocess.run([str(host.HOST_EXE)], capture_output=True, text=True)
     assert r.returncode == 0 and "Usage: ./GetHI file_name" in r.stderr
+
+
+def _tiny_param_file(tmp_path):
+    write_nutable(tmp_path / "nu.txt", 4)
+    write_param_file(tmp_path / "p.ini", n_grid=32, n_side=8, nutable=tmp_path / "nu.txt", pk_file=ROOT / "data" / "Pk_synth.dat",
+                     prefix=tmp_path / "out")
+    return tmp_path / "p.ini"
+
+
+def _no_gpu_here():
+    try:
+        import torch
+        return not torch.cuda.is_available()
+    except Exception:
+        return True
+
+
+@pytest.mark.skipif(not _no_gpu_here(), reason="checks the failure path of a box without a GPU")
+def test_fork_launcher_fails_loudly_without_a_gpu(tmp_path):
+    """GH_NGPUS=2 ./GetHI on a box with no GPU: rank 0 cannot make an NCCL id (or a context); the other rank must see
+    end-of-file on its pipe instead of waiting for ever, and the launcher must return non-zero promptly."""
+    import os
+    ini = _tiny_param_file(tmp_path)
+    r = subprocess.run([str(host.HOST_EXE), str(ini)], capture_output=True, text=True, timeout=60,
+                       env={**os.environ, "GH_NGPUS": "2"})
+    assert r.returncode != 0
+    assert "Fatal" in r.stderr
+
+
+@pytest.mark.skipif(not _no_gpu_here(), reason="checks the failure path of a box without a GPU")
+def test_launcher_environment_path_without_a_gpu(tmp_path):
+    """RANK / WORLD_SIZE / GH_UNIQUE_ID_FILE (torchrun-style launch): a non-zero rank that never gets an id file gives
+    up with a message; without GH_UNIQUE_ID_FILE the program says what is missing."""
+    import os
+    ini = _tiny_param_file(tmp_path)
+    env = {k: v for k, v in os.environ.items() if k not in ("GH_NGPUS", "GH_UNIQUE_ID_FILE")}
+    r = subprocess.run([str(host.HOST_EXE), str(ini)], capture_output=True, text=True, timeout=60,
+                       env={**env, "GH_RANK": "1", "GH_NRANKS": "2"})
+    assert r.returncode != 0 and "GH_UNIQUE_ID_FILE" in r.stderr
+    r = subprocess.run([str(host.HOST_EXE), str(ini)], capture_output=True, text=True, timeout=60,
+                       env={**env, "GH_RANK": "0", "GH_NRANKS": "2", "GH_UNIQUE_ID_FILE": str(tmp_path / "id")})
+    assert r.returncode != 0 and "Fatal" in r.stderr

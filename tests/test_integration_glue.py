@@ -52,7 +52,7 @@ def test_reference_driver_links_against_libgh_cuda_and_fails_loudly_without_a_gp
     write_nutable(tmp_path / "nu.txt", 8)
     write_param_file(tmp_path / "p.ini", n_grid=32, n_side=16, nutable=tmp_path / "nu.txt",
                      pk_file=ROOT / "data" / "Pk_synth.dat", prefix=tmp_path / "out")
-    r = subprocess.run([str(exe), str(tmp_path / "p.ini")], capture_output=True, text=True, timeout=120)
+    r = subprocess.run([str(exe), str(tmp_path / "p.ini")], capture_output=True, text=True, timeout=120, cwd=tmp_path)
     out = r.stdout + r.stderr
     assert r.returncode != 0
     assert "Reading P_k from file" in out                      # the reference's own reader and cosmology ran
