@@ -62,11 +62,13 @@ class GhCudaParams(C.Structure):
         ("nu_max", C.c_double),
         ("OmegaB", C.c_double),
         ("hhub", C.c_double),
+        ("frac_HI_arr", _dp),
+        ("bias_HI_arr", _dp),
     ]
 
 
 TABLE_FIELDS = ("logkarr", "pkarr", "z_arr_r2z", "r_arr_r2z", "growth_d_arr", "growth_v_arr",
-                "z_arr_z2r", "r_arr_z2r", "nu0_arr", "nuf_arr")
+                "z_arr_z2r", "r_arr_z2r", "nu0_arr", "nuf_arr", "frac_HI_arr", "bias_HI_arr")
 SCALAR_FIELDS = tuple(n for n, _ in GhCudaParams._fields_ if n not in TABLE_FIELDS and n != "pos_obs")
 
 

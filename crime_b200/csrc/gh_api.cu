@@ -103,7 +103,7 @@ static int upload_tables(gh_cuda_ctx *c, const gh_cuda_params *p)
   const int nz = p->nz_tab, nk = p->numk, nn = p->n_nu;
   // layout: doubles first, then floats
   const size_t n_dbl = (size_t)2 * nk + 4 * nz + 2 * nn;
-  const size_t n_flt = (size_t)4 * nz + nn + 1;
+  const size_t n_flt = (size_t)6 * nz + nn + 1;
   const size_t bytes = (n_dbl * sizeof(double) + n_flt * sizeof(float) + 7) & ~(size_t)7;
   // pinned staging, two buffers used alternately: the copy is ordered on the compute stream behind the previous
   // realisation's kernels and the host does not wait for it (a realisation can be queued while the last one runs)
@@ -132,6 +132,10 @@ static int upload_tables(gh_cuda_ctx *c, const gh_cuda_params *p)
     hf[nz + i] = (float)p->growth_d_arr[i];
     hf[2 * nz + i] = (float)p->growth_v_arr[i];
     hf[3 * nz + nn + 1 + i] = (float)p->r_arr_z2r[i];
+    // user hooks (src/user_defined.c:27-35) on the radial grid; the reference's shipped formulas when not supplied
+    const double z1 = 1.0 + p->z_arr_r2z[i];
+    hf[4 * nz + nn + 1 + i] = (float)(p->frac_HI_arr ? p->frac_HI_arr[i] : 0.008 * pow(z1, 0.6));
+    hf[5 * nz + nn + 1 + i] = (float)(p->bias_HI_arr ? p->bias_HI_arr[i] : 0.904 + 0.135 * pow(z1, 1.696));
   }
   for (int i = 0; i <= nn; ++i) {  // shell edges for the fp32 fast path
     double e;
@@ -148,6 +152,7 @@ static int upload_tables(gh_cuda_ctx *c, const gh_cuda_params *p)
   d.z_r2z = dd + o_z; d.r_r2z = dd + o_r; d.gd = dd + o_gd; d.gv = dd + o_gv;
   d.nu0 = dd + o_nu0; d.nuf = dd + o_nuf;
   d.z_r2z_f = df; d.gd_f = df + nz; d.gv_f = df + 2 * nz; d.nu_edges_f = df + 3 * nz; d.r_z2r_f = df + 3 * nz + nn + 1;
+  d.frac_f = df + 4 * nz + nn + 1; d.bias_f = df + 5 * nz + nn + 1;
   d.inv_dz_tab = (float)(1.0 / p->dz_tab); d.z_tab_max = (float)p->z_arr_z2r[nz - 1];
   return 0;
 }
@@ -258,6 +263,7 @@ static int apply_params(gh_cuda_ctx *c, const gh_cuda_params *p, int rank, int n
     for (int i = 0; i < GH_CUDA_N_SUBPART; ++i) {
       const float ox = d.sub_off_f[i], oy = d.sub_off_f[GH_CUDA_N_SUBPART + i], oz = d.sub_off_f[2 * GH_CUDA_N_SUBPART + i];
       float *m = d.sub_mono;
+      d.sub_c[i] = make_float4(ox, oy, oz, ox * ox + oy * oy + oz * oz);
       m[i] = ox * ox + oy * oy + oz * oz;
       m[GH_CUDA_N_SUBPART + i] = ox * ox - oy * oy;
       m[2 * GH_CUDA_N_SUBPART + i] = ox * oy;
@@ -476,6 +482,7 @@ extern "C" int gh_cuda_create(const gh_cuda_params *p, int rank, int nranks, con
   GH_REQUIRE(p->logkarr && p->pkarr && p->z_arr_r2z && p->r_arr_r2z && p->growth_d_arr && p->growth_v_arr &&
                  p->z_arr_z2r && p->r_arr_z2r, "gh_cuda_create: missing table pointer");
   GH_REQUIRE(!p->irregular_nutable || (p->nu0_arr && p->nuf_arr), "irregular nu table requested but not supplied");
+  GH_REQUIRE((p->frac_HI_arr == nullptr) == (p->bias_HI_arr == nullptr), "supply both frac_HI_arr and bias_HI_arr, or neither");
   if (p->irregular_nutable)
     for (int i = 0; i + 1 < p->n_nu; ++i)
       GH_REQUIRE(p->nuf_arr[i] == p->nu0_arr[i + 1], "frequency bins must be contiguous (the reference's get_inu never terminates otherwise)");
@@ -517,14 +524,14 @@ extern "C" int gh_cuda_create(const gh_cuda_params *p, int rank, int nranks, con
   } while (0)
 
   CREATE_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  c->acc_taylor = getenv("GH_ACC_TAYLOR") != nullptr;  // experimental, see accumulate_kernel
+  c->acc_taylor = getenv("GH_ACC_NO_TAYLOR") == nullptr;  // per-cell Taylor pixelisation in the equatorial belt, see accumulate_kernel
   if (getenv("GH_TIME_FFT_PASSES")) {
     for (int f = 0; f < 2; ++f)
       for (int k = 0; k < 2; ++k) CREATE_OK(cudaEventCreate(&c->ev_pass[f][k]));
     c->time_fft_passes = true;
   }
-  // one rank only for now: the fused pass has not been through the multi-GPU parity run yet
-  c->fuse_vel = nranks == 1 && getenv("GH_NO_FUSE_VEL") == nullptr;
+  // gh_cuda_run*: radial velocity and get_HI in one pass (the multi-GPU parity check compares it with the staged calls)
+  c->fuse_vel = getenv("GH_NO_FUSE_VEL") == nullptr;
   CREATE_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   CREATE_OK(cudaStreamCreateWithFlags(&c->pull_stream, cudaStreamNonBlocking));
   CREATE_OK(cudaEventCreateWithFlags(&c->ev_bar, cudaEventDisableTiming));

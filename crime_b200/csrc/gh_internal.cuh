@@ -29,6 +29,7 @@ struct GhDev {
   double glob_idr, r_tab_max;
   const double *z_r2z, *r_r2z, *gd, *gv;  // double, for the exact index path
   const float *z_r2z_f, *gd_f, *gv_f;     // float copies for the field kernels
+  const float *frac_f, *bias_f;           // fraction_HI / bias_HI on the same radial grid (src/user_defined.c:27-35)
   // sky
   long long nside, npix;
   int n_nu, n_nu_pad, irregular;
@@ -43,6 +44,8 @@ struct GhDev {
   // monomials of the float offsets for the per-cell Taylor pixelisation (GH_ACC_TAYLOR): |o|^2, ox^2-oy^2, ox*oy,
   // ox^2, oy^2, oz^2, ox*oz, oy*oz
   float sub_mono[8 * GH_CUDA_N_SUBPART];
+  // (ox, oy, oz, |o|^2) of each float offset: one 16-byte uniform load per sub-particle in the unrolled Taylor loop
+  float4 sub_c[GH_CUDA_N_SUBPART];
 };
 
 // d_partials layout (doubles): [0..1] sum, sum of squares (all-reduced); [4] mean; [5] measured variance;
@@ -81,7 +84,7 @@ struct gh_cuda_ctx {
   bool have_peers;                 // peer mappings established (nranks>1, same node)
   bool time_fft_passes;            // opt-in (GH_TIME_FFT_PASSES=1): events around each field's z pass + transpose
   cudaEvent_t ev_pass[2][2];
-  bool acc_taylor;                 // opt-in (GH_ACC_TAYLOR=1): per-cell Taylor pixelisation in the equatorial belt
+  bool acc_taylor;                 // per-cell Taylor pixelisation in the equatorial belt (GH_ACC_NO_TAYLOR=1 turns it off)
   bool fuse_vel;                   // gh_cuda_run*: radial velocity and get_HI in one pass
   bool sparse_reduce;              // opt-in: map reduction by pulling the peers' touched pixel intervals (GH_SPARSE_REDUCE=1)
   float *map_peers[GH_MAX_RANKS];  // every rank's accumulation stack (peer-mapped), sparse_reduce only

@@ -99,6 +99,7 @@ __device__ __forceinline__ float r_of_z_f(const FastCtx &f, float z)
 struct CellShells {
   float lo_a, hi_a, lo_b, hi_b;
   int shell[3];
+  int j_in;  // shell[k] == shell_or_out(j_in - k): the shells in reach are consecutive, decreasing with radius
   bool ok;
 };
 
@@ -108,6 +109,7 @@ __device__ __forceinline__ CellShells cell_shells(const FastCtx &f, float zs_lo,
   c.ok = false;
   c.lo_a = c.hi_a = c.lo_b = c.hi_b = 3.0e38f;
   c.shell[0] = c.shell[1] = c.shell[2] = -1;
+  c.j_in = -1;
   const float nu_hi = 1420.40575177f * rcp_ftz(1.0f + zs_lo), nu_lo = 1420.40575177f * rcp_ftz(1.0f + zs_hi);
   // j_min = first edge >= nu_lo
   int j = (int)ceilf((nu_lo - f.nu_min) * f.inv_dnu);
@@ -126,8 +128,10 @@ __device__ __forceinline__ CellShells cell_shells(const FastCtx &f, float zs_lo,
   auto shell_or_out = [&](int g) { return (g >= 0 && g < f.n_nu) ? g : -1; };
   if (ne == 0) {
     c.shell[0] = shell_or_out(j - 1);
+    c.j_in = j - 1;
   } else {
     const int j_in = j + ne - 1;  // highest-frequency edge in reach = smallest radius
+    c.j_in = j_in;
     {
       const float r = r_of_z_f(f, 1420.40575177f * rcp_ftz(__ldg(f.edges + j_in)) - 1.0f - dz);
       const float a = fmaxf(r - f.eps_r, 0.f), b = r + f.eps_r;
@@ -217,15 +221,21 @@ __device__ __forceinline__ bool fast_pixel(const FastCtx &f, float cth, float tt
 // Planes: the launch covers gridDim.z consecutive planes; plane blockIdx.z sits at local index iz_base +
 // blockIdx.z of the buffers passed in and is global plane zg_base + blockIdx.z (this rank's own slab, or planes
 // pulled from a neighbour for load balance -- see enqueue_maps in gh_api.cu).
-// TAYLOR (opt-in, GH_ACC_TAYLOR=1; written after this round's GPU budget was spent -- not yet audited on hardware):
-// cells whose sub-particles all lie in HEALPix's equatorial belt get the two ring coordinates
-// A = ns*(tt + 1/2) and B = (3/4) ns cos(theta) from a second-order Taylor expansion about the cell centre.  The
-// ten offsets are the same for every cell, so their monomials are constants and a sub-particle costs 4 + 9 FMAs
-// for (A, B) and 3 for r^2, instead of positions, rsqrt, the azimuth series and cos(theta).  The third-order
-// remainder, <= ns*(0.2123 (d/rho)^3 + 0.375 (d/r)^3) with d the half cell diagonal (tools/taylor_proto.py), is
-// added to the confidence margin of the cell.
+// TAYLOR (default; GH_ACC_NO_TAYLOR=1 turns it off): cells whose sub-particles all lie in HEALPix's equatorial belt
+// (two thirds of the sky) get the two ring coordinates A = ns*(tt + 1/2) and B = (3/4) ns cos(theta) from a
+// second-order Taylor expansion about the cell centre.  The ten offsets are the same for every cell, so their
+// monomials are kernel-parameter constants: the loop is fully unrolled and a sub-particle costs 5 + 10 FMAs for
+// (A, B) and 4 for r^2 with constant-bank multipliers, instead of positions, rsqrt, the azimuth series and
+// cos(theta).  The third-order remainder, <= ns*(0.2123 (d/rho)^3 + 0.375 (d/r)^3) with d the half cell diagonal
+// (tools/taylor_proto.py, tests/test_taylor_pixelisation_cpu.py), is added to the confidence margin of the cell.
+// Audited on the device against the exact path at margin scales 1, 1/2, 1/4 (0 disagreements; profiles/).
+// 8 resident CTAs (64 registers): measured at 512^3 / 1024^3 the stage slows down steeply with more registers per thread
+// (99 regs: 6.3 ms, 80: 4.8, 64: 4.2 -- profiles/r2/ab_accumulate_*.log): its long prologue chains need the warps
+#ifndef GH_ACC_MIN_BLOCKS
+#define GH_ACC_MIN_BLOCKS 8
+#endif
 template <bool AUDIT, bool TAYLOR>
-__global__ void __launch_bounds__(128) accumulate_kernel(GhDev d, const float *__restrict__ mass,
+__global__ void __launch_bounds__(128, GH_ACC_MIN_BLOCKS) accumulate_kernel(GhDev d, const float *__restrict__ mass,
                                                          const float *__restrict__ dzrsd, float *__restrict__ maps,
                                                          float eps_scale, unsigned long long *__restrict__ counts,
                                                          int iz_base, int zg_base)
@@ -272,8 +282,7 @@ __global__ void __launch_bounds__(128) accumulate_kernel(GhDev d, const float *_
       }
     }
     if (!culled) {
-      const double mass_sub = (double)cell_mass / GH_CUDA_N_SUBPART;  // src/pixelize.c:203
-      w = (float)mass_sub;
+      w = __fdiv_rn(cell_mass, (float)GH_CUDA_N_SUBPART);  // src/pixelize.c:203: float / int is a float division in C
       // azimuth of the cell centre; sub-particles rotate it by atan(cross/dot), |cross/dot| < 0.05 when
       // the cell is further than 24 cells from the polar axis
       const bool series = rp2 > 576.0f * (float)(d.dx * d.dx);
@@ -281,18 +290,25 @@ __global__ void __launch_bounds__(128) accumulate_kernel(GhDev d, const float *_
       const CellShells cs = cell_shells(f, zs_lo, zs_hi, dzf);
       bool lean = false;
       if constexpr (TAYLOR) {
-        const float inv_rc = rsqrt_ftz(fmaf(zh, zh, rp2));
-        // every sub-particle of the cell in the equatorial belt (|d cos(theta)| <= d/r), away from the tt wrap,
-        // and the cell's shells known as r^2 thresholds
-        lean = cs.ok && series && (fabsf(zh) * inv_rc + h * inv_rc < f.cth_lo) && (fabsf(yh) > 2.0f * h || xh < 0.f);
+        const float inv_rc = rsqrt_ftz(fmaf(zh, zh, rp2)), inv_rho = rsqrt_ftz(rp2);
+        // third-order remainder of both expansions (h = half cell diagonal + slack), on top of the fp32 margin
+        const float fns = f.fns, dr = h * inv_rc, drho = h * inv_rho;
+        const float e_cell = f.eidx + fns * fmaf(0.2123f * drho, drho * drho, 0.375f * dr * dr * dr);
+        // every sub-particle of the cell in the equatorial belt (|d cos(theta)| <= d/r), the cell's shells known as
+        // r^2 thresholds, and every sub-particle's azimuth clear of the tt = 0 / 4 seam by more than the margins
+        // (|y| > h for all of them when x > 0, so tt and 4 - tt exceed (2/pi) atan(h/(rho+h)) > 0.3 h/rho)
+        lean = cs.ok && series && (fabsf(zh) * inv_rc + dr < f.cth_lo) &&
+               (xh < -h || (fabsf(yh) > 2.0f * h && 0.3f * drho * fns > fns * f.eps_tt + e_cell));
         if (lean) {
-          const float fns = f.fns, irho2 = rcp_ftz(rp2), ir2 = inv_rc * inv_rc, ir3 = inv_rc * ir2, ir5 = ir3 * ir2;
+          const float irho2 = inv_rho * inv_rho, ir2 = inv_rc * inv_rc, ir3 = inv_rc * ir2, ir5 = ir3 * ir2;
           const float k = 0.63661977236758134308f * fns, kq = k * irho2 * irho2, c34 = 0.75f * fns;
           float ttc = phi_c * 0.63661977236758134308f;
           ttc += (ttc < 0.f) ? 4.0f : 0.f;
+          // A = A0 + Ax ox + Ay oy + Axx (ox^2 - oy^2) + Axy ox oy, evaluated as A0 + oy (Ay - Axx oy) + ox (Ax + Axx ox + Axy oy)
           const float Ax = -k * yh * irho2, Ay = k * xh * irho2;
-          const float Axx = kq * xh * yh, Axy = kq * fmaf(yh, yh, -xh * xh);
+          const float Axx = kq * xh * yh, nAxx = -Axx, Axy = kq * fmaf(yh, yh, -xh * xh);
           const float A0 = fmaf(Ax, xl, fmaf(Ay, yl, fmaf(fns, ttc, 0.5f * fns)));
+          // B = B0 + oz (Bz + Bzz oz) + oy (By + Byy oy + Byz oz) + ox (Bx + Bxx ox + Bxy oy + Bxz oz)
           const float zi3 = zh * ir3, t3 = 3.0f * zh * ir5;
           const float Bx = -c34 * xh * zi3, By = -c34 * yh * zi3, Bz = c34 * rp2 * ir3;
           const float Bxx = 0.5f * c34 * fmaf(t3 * xh, xh, -zi3), Byy = 0.5f * c34 * fmaf(t3 * yh, yh, -zi3);
@@ -301,47 +317,50 @@ __global__ void __launch_bounds__(128) accumulate_kernel(GhDev d, const float *_
           const float B0 = fmaf(Bx, xl, fmaf(By, yl, fmaf(Bz, zl, c34 * zh * inv_rc)));
           const float r2c = fmaf(2.0f * xh, xl, fmaf(2.0f * yh, yl, fmaf(2.0f * zh, zl, fmaf(zh, zh, rp2))));
           const float x2 = 2.0f * xh, y2 = 2.0f * yh, z2 = 2.0f * zh;
-          // third-order remainder of both expansions (h = half cell diagonal + slack), on top of the fp32 margin
-          const float dr = h * inv_rc, drho = h * rsqrt_ftz(rp2);
-          const float e_cell = f.eidx + fns * fmaf(0.2123f * drho, drho * drho, 0.375f * dr * dr * dr);
           const float m_lo = e_cell, m_hi = 1.0f - e_cell;
-          const float a_lo = 0.5f * fns + fns * f.eps_tt + e_cell, a_hi = 4.5f * fns - fns * f.eps_tt - e_cell;
-          const int ns = f.ns;
-          const float *M = d.sub_mono;
-#pragma unroll 2
+          const int ns = f.ns, ns4 = 4 * ns, n_nu = f.n_nu, j_in = cs.j_in, npix32 = (int)d.npix;
+          int pix0 = 2 * ns * (ns - 1) + ns * ns4;                // pix = pix0 + (jp - jm) * 4 ns + ip
+          const float lo_a = cs.lo_a, hi_a = cs.hi_a, lo_b = cs.lo_b, hi_b = cs.hi_b;
+          // global address of shell j_in's map (never dereferenced out of range).  Opaque to the optimiser from here on:
+          // otherwise it folds base and pix0 back into every sub-particle's address arithmetic (a 64-bit multiply and two
+          // more integer operations per deposit) instead of keeping them in registers
+          unsigned long long shell_base = (unsigned long long)__cvta_generic_to_global(maps) + 4ull * (unsigned long long)((long long)d.npix * j_in);
+          asm volatile("" : "+l"(shell_base), "+r"(pix0));
+          // fully unrolled: the ten offsets (x, y, z, |o|^2) are kernel-parameter constants, one 16-byte uniform load each
+#pragma unroll
           for (int isub = 0; isub < GH_CUDA_N_SUBPART; ++isub) {
-            const float ox = d.sub_off_f[isub], oy = d.sub_off_f[GH_CUDA_N_SUBPART + isub], oz = d.sub_off_f[2 * GH_CUDA_N_SUBPART + isub];
-            const float r2 = r2c + fmaf(x2, ox, fmaf(y2, oy, fmaf(z2, oz, M[isub])));
-            const bool in0 = r2 < cs.lo_a, in1 = (r2 > cs.hi_a) & (r2 < cs.lo_b), in2 = r2 > cs.hi_b;
-            int inu = in0 ? cs.shell[0] : (in1 ? cs.shell[1] : cs.shell[2]);
-            int st = (in0 | in1 | in2) ? (inu >= 0 ? GH_FAST_IN : GH_FAST_OUT) : GH_FAST_UNSURE;
-            int pix = -1;
-            if (st == GH_FAST_IN) {
-              const float A = fmaf(Ax, ox, fmaf(Ay, oy, fmaf(Axx, M[GH_CUDA_N_SUBPART + isub], fmaf(Axy, M[2 * GH_CUDA_N_SUBPART + isub], A0))));
-              const float B = fmaf(Bx, ox, fmaf(By, oy, fmaf(Bz, oz, fmaf(Bxx, M[3 * GH_CUDA_N_SUBPART + isub],
-                              fmaf(Byy, M[4 * GH_CUDA_N_SUBPART + isub], fmaf(Bzz, M[5 * GH_CUDA_N_SUBPART + isub],
-                              fmaf(Bxy, M[2 * GH_CUDA_N_SUBPART + isub], fmaf(Bxz, M[6 * GH_CUDA_N_SUBPART + isub],
-                              fmaf(Byz, M[7 * GH_CUDA_N_SUBPART + isub], B0)))))))));
-              const float a = A - B, b = A + B;
-              const float fa = floorf(a), fb = floorf(b);
-              const float ra = a - fa, rb = b - fb;
-              const bool ok = (ra > m_lo) & (ra < m_hi) & (rb > m_lo) & (rb < m_hi) & (A > a_lo) & (A < a_hi);
-              const int jp = (int)fa, jm = (int)fb;
-              const int ir = ns + 1 + jp - jm;
-              int ip = (jp + jm - ns + 2 - (ir & 1)) >> 1;
-              ip -= (ip >= 4 * ns) ? 4 * ns : 0;
-              pix = 2 * ns * (ns - 1) + (ir - 1) * 4 * ns + ip;
-              if (!ok) st = GH_FAST_UNSURE;
-            }
+            const float4 o = d.sub_c[isub];
+            const float r2 = fmaf(x2, o.x, fmaf(y2, o.y, fmaf(z2, o.z, r2c + o.w)));
+            // shell: j_in inside the inner edge, one less beyond each edge crossed; unsure within eps_r of an edge
+            const bool p1 = r2 > hi_a, p2 = r2 > hi_b;
+            const bool sure = ((r2 < lo_a) || p1) && ((r2 < lo_b) || p2);
+            const int inu = j_in - (p1 ? 1 : 0) - (p2 ? 1 : 0);
+            const bool inside = (unsigned)inu < (unsigned)n_nu;
+            const float A = fmaf(o.x, fmaf(Axy, o.y, fmaf(Axx, o.x, Ax)), fmaf(o.y, fmaf(nAxx, o.y, Ay), A0));
+            const float B = fmaf(o.x, fmaf(Bxz, o.z, fmaf(Bxy, o.y, fmaf(Bxx, o.x, Bx))),
+                                 fmaf(o.y, fmaf(Byz, o.z, fmaf(Byy, o.y, By)), fmaf(o.z, fmaf(Bzz, o.z, Bz), B0)));
+            const float a = A - B, b = A + B;
+            const float fa = floorf(a), fb = floorf(b);
+            const float ra = a - fa, rb = b - fb;
+            const bool ok = (ra > m_lo) && (ra < m_hi) && (rb > m_lo) && (rb < m_hi);
+            const int jp = (int)fa, jm = (int)fb;
+            // ir - 1 = ns + jp - jm;  ip = (jp + jm - ns + kshift + 1) / 2 with kshift = 1 - (ir & 1): jp + jm - ns + 1
+            // has the parity of ir, so the division is (jp + jm - ns + 1) >> 1 for either parity
+            int ip = (jp + jm - ns + 1) >> 1;
+            ip -= (ip >= ns4) ? ns4 : 0;
+            const int pix = pix0 + (jp - jm) * ns4 + ip;
             if (!AUDIT) {
-              if (st == GH_FAST_IN) atomicAdd(maps + ((size_t)d.npix * inu + pix), w);
-              else if (st == GH_FAST_UNSURE) need |= 1u << isub;
+              if (sure && inside && ok) {
+                const int rel = pix - (p1 ? npix32 : 0) - (p2 ? npix32 : 0);
+                asm volatile("red.global.add.f32 [%0], %1;" ::"l"(shell_base + 4ll * (long long)rel), "f"(w));
+              }
+              else if (!sure || inside) need |= 1u << isub;  // sure && !inside: surely outside every shell
             } else {
               long long pe;
               const int se = gh_point_to_shell_pixel(t, x0 + d.sub_off[isub], y0 + d.sub_off[GH_CUDA_N_SUBPART + isub],
                                                      z0 + d.sub_off[2 * GH_CUDA_N_SUBPART + isub], (double)dzf, &pe);
-              if (st == GH_FAST_OUT) { c_out++; if (pe >= 0) c_wrong++; }
-              else if (st == GH_FAST_IN) { c_in++; if (inu != se || (long long)pix != pe) c_wrong++; }
+              if (sure && !inside) { c_out++; if (pe >= 0) c_wrong++; }
+              else if (sure && ok) { c_in++; if (inu != se || (long long)pix != pe) c_wrong++; }
               else c_unsure++;
             }
           }
@@ -423,7 +442,8 @@ __global__ void __launch_bounds__(128) accumulate_kernel(GhDev d, const float *_
     const double px = d.dx * (sx + 0.5) - d.pos_obs[0] + d.sub_off[isub];
     const double py = d.dx * (sy + 0.5) - d.pos_obs[1] + d.sub_off[GH_CUDA_N_SUBPART + isub];
     long long ipix;
-    const int inu = gh_point_to_shell_pixel(t, px, py, z0 + d.sub_off[2 * GH_CUDA_N_SUBPART + isub], (double)s_dz[src], &ipix);
+    const double pz = d.dx * (zg + 0.5) - d.pos_obs[2] + d.sub_off[2 * GH_CUDA_N_SUBPART + isub];  // z0 again: nothing of the prologue stays live
+    const int inu = gh_point_to_shell_pixel(t, px, py, pz, (double)s_dz[src], &ipix);
     if (ipix >= 0) atomicAdd(maps + (size_t)ipix + (size_t)d.npix * inu, s_w[src]);
   }
 }

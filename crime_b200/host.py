@@ -14,7 +14,7 @@ from . import abi
 HOST_LIB = abi.REPO_ROOT / "host" / "libgh_host.so"
 HOST_EXE = abi.REPO_ROOT / "host" / "GetHI"
 _TABLES = ("logkarr", "pkarr", "z_arr_z2r", "r_arr_z2r", "z_arr_r2z", "r_arr_r2z", "growth_d_arr", "growth_v_arr",
-           "nu0_arr", "nuf_arr")
+           "nu0_arr", "nuf_arr", "frac_HI_arr", "bias_HI_arr")
 _SCALARS = ("n_grid", "l_box", "seed_rng", "do_smoothing", "r2_smooth", "fgrowth_0", "hubble_0", "numk", "logkmin",
             "logkmax", "idlogk", "n_scal", "nz_tab", "glob_idr", "dz_tab", "n_side", "n_nu", "irregular_nutable",
             "nu_min", "nu_max", "OmegaB", "hhub", "z_min", "z_max", "r_min", "r_max")

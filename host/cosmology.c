@@ -233,8 +233,10 @@ void cosmo_set(ParamGetHI *par)
     par->growth_v_arr[i] = gz * hubble_of_a(&bg, a) * fgrowth_of_a(&bg, a, alim) / (par->fgrowth_0 * par->hubble_0);
   }
   if (par->z_arr_r2z[GH_NZ - 1] <= par->z_max || par->r_arr_r2z[GH_NZ - 1] <= par->r_max) report_error(1, "OMG!\n");
+  /* the user hooks (host/user_defined.c) on the radial grid: get_HI on the device interpolates these */
+  for (int i = 0; i < GH_NZ; i++) {
+    par->frac_HI_arr[i] = fraction_HI(par->z_arr_r2z[i]);
+    par->bias_HI_arr[i] = bias_HI(par->z_arr_r2z[i]);
+  }
   read_pk(par);
 }
-
-double fraction_HI(double z) { return 0.008 * pow(1 + z, 0.6); }
-double bias_HI(double z) { return 0.904 + 0.135 * pow(1 + z, 1.696); }

@@ -34,6 +34,8 @@ typedef struct ParamGetHI {
   double *logkarr, *pkarr;
   double z_arr_z2r[GH_NZ], r_arr_z2r[GH_NZ], z_arr_r2z[GH_NZ], r_arr_r2z[GH_NZ];
   double growth_d_arr[GH_NZ], growth_v_arr[GH_NZ];
+  /* fraction_HI / bias_HI (user_defined.c) sampled at z_arr_r2z: how the user hooks reach the device */
+  double frac_HI_arr[GH_NZ], bias_HI_arr[GH_NZ];
   double glob_idr;
   unsigned int seed_rng;
   int irregular_nutable; /* the reference's -D_IRREGULAR_NUTABLE compile-time personality, here a run-time flag */

@@ -24,6 +24,7 @@ void gh_fill_cuda_params(const ParamGetHI *par, gh_cuda_params *p)
   p->n_side = par->n_side; p->n_nu = par->n_nu; p->irregular_nutable = par->irregular_nutable;
   p->nu0_arr = par->nu0_arr; p->nuf_arr = par->nuf_arr; p->nu_min = par->nu_min; p->nu_max = par->nu_max;
   p->OmegaB = par->OmegaB; p->hhub = par->hhub;
+  p->frac_HI_arr = par->frac_HI_arr; p->bias_HI_arr = par->bias_HI_arr;
 }
 
 static void check(int rc, const char *what)

@@ -26,6 +26,7 @@ const double *gh_param_table(const ParamGetHI *p, const char *name, int *len)
   T("z_arr_z2r", p->z_arr_z2r, GH_NZ) T("r_arr_z2r", p->r_arr_z2r, GH_NZ)
   T("z_arr_r2z", p->z_arr_r2z, GH_NZ) T("r_arr_r2z", p->r_arr_r2z, GH_NZ)
   T("growth_d_arr", p->growth_d_arr, GH_NZ) T("growth_v_arr", p->growth_v_arr, GH_NZ)
+  T("frac_HI_arr", p->frac_HI_arr, GH_NZ) T("bias_HI_arr", p->bias_HI_arr, GH_NZ)
   T("nu0_arr", p->nu0_arr, p->nu0_arr ? p->n_nu : 0) T("nuf_arr", p->nuf_arr, p->nuf_arr ? p->n_nu : 0)
 #undef T
   *len = 0;

@@ -70,6 +70,12 @@ typedef struct gh_cuda_params {
   const double *nuf_arr; /* [n_nu] upper edges (irregular only) */
   double nu_min, nu_max;
   double OmegaB, hhub;
+  /* the user hooks of src/user_defined.c:27-35 (a file GetHI users are told to edit), tabulated by the host on the
+   * radial grid: frac_HI_arr[i] = fraction_HI(z_arr_r2z[i]), bias_HI_arr[i] = bias_HI(z_arr_r2z[i]).  get_HI
+   * interpolates them in r exactly like the redshift and growth tables (src/cosmo.c:52-86).  NULL (both): the
+   * formulas the reference ships, x_HI = 0.008 (1+z)^0.6 and b_HI = 0.904 + 0.135 (1+z)^1.696. */
+  const double *frac_HI_arr; /* [nz_tab] or NULL */
+  const double *bias_HI_arr; /* [nz_tab] or NULL */
 } gh_cuda_params;
 
 typedef struct gh_cuda_ctx gh_cuda_ctx;

@@ -16,6 +16,8 @@ HERE = Path(__file__).resolve().parent
 ORACLE_SO = HERE / "liboracle.so"
 REF_SO = HERE / "_ref" / "libgethi_ref.so"
 REF_SO_REGULAR = HERE / "_ref" / "libgethi_ref_regular.so"  # built without -D_IRREGULAR_NUTABLE
+REF_SO_USERDEF = HERE / "_ref" / "libgethi_ref_userdef.so"  # user_defined.c swapped for oracle/userdef_variant.c
+USERDEF_VARIANT = dict(a=0.012, p=0.3, b0=1.1, b1=0.07, q=2.1)  # the numbers in oracle/userdef_variant.c
 REF_EXE = HERE / "_ref" / "GetHI"
 REFERENCE_ROOT = Path(os.environ.get("CRIME_REFERENCE", "/root/reference"))
 
@@ -58,6 +60,7 @@ class Oracle:
         for name in ("oracle_fraction_HI", "oracle_bias_HI"):
             getattr(lib, name).argtypes = [_d]
             getattr(lib, name).restype = _d
+        lib.oracle_set_user_defined.argtypes = [_d, _d, _d, _d, _d]
         lib.oracle_kgen_mt19937.argtypes = [_pp, Slab, _i, _vp, _vp]
         lib.oracle_kgen_philox.argtypes = [_pp, _i, _i, _vp, _vp, _i]
         lib.oracle_philox4x32_10.argtypes = [_vp, _vp, _vp]
@@ -156,6 +159,10 @@ class Oracle:
         self.lib.oracle_get_HI(C.byref(p), Slab(d.shape[0], iz0), sigma2, _ptr(d), _ptr(v))
         return d, v
 
+    def set_user_defined(self, a=0.008, p=0.6, b0=0.904, b1=0.135, q=1.696):
+        """x_HI = a (1+z)^p, b_HI = b0 + b1 (1+z)^q (user_defined.c:27-35); no arguments: the shipped model."""
+        self.lib.oracle_set_user_defined(a, p, b0, b1, q)
+
     def subparticle_offsets(self, p) -> np.ndarray:
         out = np.zeros(3 * N_SUBPART)
         self.lib.oracle_subparticle_offsets(C.byref(p), _ptr(out))
@@ -216,9 +223,10 @@ class Reference:
     def available(regular: bool = False) -> bool:
         return (REF_SO_REGULAR if regular else REF_SO).exists()
 
-    def __init__(self, regular: bool = False):
-        """regular=True: the build without -D_IRREGULAR_NUTABLE (param keys nu_min / nu_max / n_nu)."""
-        so = REF_SO_REGULAR if regular else REF_SO
+    def __init__(self, regular: bool = False, userdef: bool = False):
+        """regular=True: the build without -D_IRREGULAR_NUTABLE (param keys nu_min / nu_max / n_nu);
+        userdef=True: the build with oracle/userdef_variant.c in place of the reference's user_defined.c."""
+        so = REF_SO_USERDEF if userdef else (REF_SO_REGULAR if regular else REF_SO)
         self.regular = regular
         if not so.exists():
             raise RuntimeError(f"{so} missing (needs the reference tree to build; see oracle/Makefile)")

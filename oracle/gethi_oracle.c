@@ -46,8 +46,13 @@ double oracle_z_of_r(const gh_cuda_params *p, double r) { return lerp_r(p, p->z_
 double oracle_dgrowth_of_r(const gh_cuda_params *p, double r) { return lerp_r(p, p->growth_d_arr, r, 1); } /* cosmo.c:64-74 */
 double oracle_vgrowth_of_r(const gh_cuda_params *p, double r) { return lerp_r(p, p->growth_v_arr, r, 1); } /* cosmo.c:76-86 */
 
-double oracle_fraction_HI(double z) { return 0.008 * pow(1 + z, 0.6); }        /* user_defined.c:27-30 */
-double oracle_bias_HI(double z) { return 0.904 + 0.135 * pow(1 + z, 1.696); }  /* user_defined.c:32-35 */
+/* user_defined.c:27-35 -- a file the reference tells its users to edit.  The shipped functions are
+ * x_HI = a (1+z)^p and b_HI = b0 + b1 (1+z)^q; oracle_set_user_defined changes the five numbers so that the tests can
+ * follow a user's edit (pinned by the reference compiled with oracle/userdef_variant.c in place of its user_defined.c). */
+static double ud_a = 0.008, ud_p = 0.6, ud_b0 = 0.904, ud_b1 = 0.135, ud_q = 1.696;
+void oracle_set_user_defined(double a, double p, double b0, double b1, double q) { ud_a = a; ud_p = p; ud_b0 = b0; ud_b1 = b1; ud_q = q; }
+double oracle_fraction_HI(double z) { return ud_a * pow(1 + z, ud_p); }        /* user_defined.c:27-30 */
+double oracle_bias_HI(double z) { return ud_b0 + ud_b1 * pow(1 + z, ud_q); }  /* user_defined.c:32-35 */
 
 /* ------------------------------------------------------------------ k-space realisation */
 
@@ -141,7 +146,9 @@ void oracle_kgen_philox(const gh_cuda_params *p, int ky0, int nky, float _Comple
         r[0] = r4[2 * (gidx & 1)];
         r[1] = r4[2 * (gidx & 1) + 1];
         size_t o = ((size_t)ii * nky + jl) * nh + kk;
-        mode_from_uniforms(p, k2, idk3, factor, (r[0] >> 8) / 16777216.0, (r[1] >> 8) / 16777216.0, &dens_k[o], &vpot_k[o]);
+        /* phase from 24 bits; the modulus draw keeps all 32 bits, like gsl_rng_uniform (u32 / 2^32, src/common.c:154-164):
+         * a 24-bit u2 would clip the Rayleigh tail at sqrt(ln 2^24) = 4.08 sigma_k */
+        mode_from_uniforms(p, k2, idk3, factor, (r[0] >> 8) / 16777216.0, r[1] / 4294967296.0, &dens_k[o], &vpot_k[o]);
       }
     }
   }

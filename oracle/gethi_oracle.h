@@ -27,6 +27,7 @@ double oracle_r_of_z(const gh_cuda_params *p, double z);          /* cosmo.c:40-
 double oracle_z_of_r(const gh_cuda_params *p, double r);          /* cosmo.c:52-62 */
 double oracle_dgrowth_of_r(const gh_cuda_params *p, double r);    /* cosmo.c:64-74 */
 double oracle_vgrowth_of_r(const gh_cuda_params *p, double r);    /* cosmo.c:76-86 */
+void oracle_set_user_defined(double a, double p, double b0, double b1, double q); /* default: the shipped 0.008, 0.6, 0.904, 0.135, 1.696 */
 double oracle_fraction_HI(double z);                              /* user_defined.c:27-30 */
 double oracle_bias_HI(double z);                                  /* user_defined.c:32-35 */
 

@@ -3,6 +3,7 @@
 #include "gh_cuda.h"
 
 static gh_cuda_ctx *ctx;
+static double frac_tab[NZ], bias_tab[NZ];                            /* user_defined.c on the radial grid */
 
 static void fill(const ParamGetHI *par, gh_cuda_params *p)          /* ParamGetHI -> POD mirror */
 {
@@ -22,6 +23,11 @@ static void fill(const ParamGetHI *par, gh_cuda_params *p)          /* ParamGetH
   p->irregular_nutable = 1; p->nu0_arr = par->nu0_arr; p->nuf_arr = par->nuf_arr;
 #endif
   p->OmegaB = par->OmegaB; p->hhub = par->hhub;
+  for (int i = 0; i < NZ; i++) {                                     /* edits to user_defined.c reach the device */
+    frac_tab[i] = fraction_HI(par->z_arr_r2z[i]);
+    bias_tab[i] = bias_HI(par->z_arr_r2z[i]);
+  }
+  p->frac_HI_arr = frac_tab; p->bias_HI_arr = bias_tab;
 }
 
 void init_fftw(ParamGetHI *par)                       /* src/fourier.c:101 */

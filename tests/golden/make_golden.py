@@ -112,8 +112,44 @@ def run_regular_case(tmp, name, n_grid, n_side, n_nu, seed, nu_min=355.0, nu_max
     print(name, "written", (HERE / f"{name}.npz").stat().st_size // 1024, "KiB")
 
 
+def run_userdef_case(tmp, name, n_grid, n_side, n_nu, seed):
+    """get_HI of the reference compiled with oracle/userdef_variant.c instead of its own user_defined.c (the file users
+    are told to edit): inputs (Gaussian density, radial velocity, variance) and outputs (HI mass, Delta z_RSD)."""
+    from oracle.binding import USERDEF_VARIANT
+    ref = Reference(userdef=True)
+    nut, ini = f"{tmp}/nu_{name}.txt", f"{tmp}/{name}.ini"
+    write_nutable(nut, n_nu)
+    write_param_file(ini, n_grid=n_grid, n_side=n_side, nutable=nut, pk_file=str(ROOT / "data" / "Pk_synth.dat"),
+                     prefix=f"{tmp}/{name}", seed=seed)
+    par = ref.read_run_params(ini)
+    d = ref.params_dict(par)
+    out = {k: np.asarray(d[k]) for k in SCALARS}
+    out["pos_obs"] = np.asarray(d["pos_obs"])
+    for t in Reference.TABLES:
+        out[t] = d[t]
+    out["omp_threads"] = np.asarray(int(os.environ["OMP_NUM_THREADS"]))
+    n, nh = n_grid, n_grid // 2 + 1
+    rs = (n, n, 2 * nh)
+    ref.lib.ref_create_d_and_vr_fields(par)
+    out["dens"] = ref.grid(par, "dens", rs).copy()
+    out["rvel"] = ref.grid(par, "rvel", rs).copy()
+    out["sigma2_gauss"] = np.asarray(ref.get(par, "sigma2_gauss"))
+    ref.lib.ref_get_HI(par)
+    out["mass"] = ref.grid(par, "dens", rs).copy()
+    out["dz_rsd"] = ref.grid(par, "rvel", rs).copy()
+    for k in ("dens", "rvel", "mass", "dz_rsd"):
+        out[k][:, :, n:] = 0
+    zz = np.linspace(0.0, 5.0, 501)
+    out["probe_z"] = zz
+    out["probe_bias"] = np.array([ref.lib.ref_bias_HI(z) for z in zz])
+    out["probe_frac"] = np.array([ref.lib.ref_fraction_HI(z) for z in zz])
+    out["userdef"] = np.array([USERDEF_VARIANT[k] for k in ("a", "p", "b0", "b1", "q")])
+    np.savez_compressed(HERE / f"{name}.npz", **out)
+    print(name, "written", (HERE / f"{name}.npz").stat().st_size // 1024, "KiB")
+
+
 def main():
-    """no argument: every fixture; `regular`: only ref_n32_regular.npz (leaves the others untouched)."""
+    """no argument: every fixture; `regular` / `userdef`: only that fixture (leaves the others untouched)."""
     if "OMP_NUM_THREADS" not in os.environ:
         raise SystemExit("set OMP_NUM_THREADS (the realisation depends on it)")
     only = sys.argv[1] if len(sys.argv) > 1 else ""
@@ -126,6 +162,8 @@ def main():
             run_case(ref, tmp, "ref_tables_nu150", n_grid=1024, n_side=512, n_nu=150, seed=1001, full=False)
         if only in ("", "regular"):
             run_regular_case(tmp, "ref_n32_regular", n_grid=32, n_side=16, n_nu=20, seed=1001)
+        if only in ("", "userdef"):
+            run_userdef_case(tmp, "ref_n32_userdef", n_grid=32, n_side=16, n_nu=16, seed=1001)
 
 
 if __name__ == "__main__":

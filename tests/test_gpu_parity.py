@@ -695,3 +695,30 @@ def test_statistical_acceptance_of_the_device_realisation(tables_nu64, seed):
         json.dump({"kspace": {k: (v if k != "zero_mode" else abs(v)) for k, v in kr.items()}, "one_point": one,
                    "lognormal_mean": lm[0], "lognormal_mean_sigma": lm[1], "sigma2_gauss": s2}, f, indent=1)
     sc.assert_acceptance(kr, one, *lm)
+
+
+def test_user_defined_hooks_reach_the_device():
+    """fraction_HI / bias_HI (src/user_defined.c:27-35, a file users are told to edit) cross the boundary as two radial
+    tables.  With the tables of a different HI model (oracle/userdef_variant.c) get_HI must reproduce the reference
+    compiled with that model (tests/golden/ref_n32_userdef.npz); without tables it computes the shipped model."""
+    from conftest import GOLDEN
+    from crime_b200 import GetHI
+    from crime_b200.abi import GRID_DENS, GRID_RVEL, params_from_dict, params_to_dict
+    g = dict(np.load(GOLDEN / "ref_n32_userdef.npz"))
+    a, pw, b0, b1, q = (float(x) for x in g["userdef"])
+    d = params_to_dict(params_of(g))
+    z = np.asarray(d["z_arr_r2z"])
+    d["frac_HI_arr"] = a * (1 + z) ** pw
+    d["bias_HI_arr"] = b0 + b1 * (1 + z) ** q
+    n = 32
+    out = {}
+    for tag, dd in (("variant", d), ("shipped", {k: v for k, v in d.items() if k not in ("frac_HI_arr", "bias_HI_arr")})):
+        with GetHI(params_from_dict(dd)) as gh:
+            gh.upload_grid(GRID_DENS, g["dens"])
+            gh.upload_grid(GRID_RVEL, g["rvel"])
+            gh.set_sigma2_gauss(float(g["sigma2_gauss"]))
+            gh.get_HI()
+            out[tag] = (gh.download_grid(GRID_DENS)[:, :, :n], gh.download_grid(GRID_RVEL)[:, :, :n])
+    assert np.abs(out["variant"][0] / g["mass"][:, :, :n] - 1).max() < TOL
+    assert field_err(out["variant"][1], g["dz_rsd"][:, :, :n]) < TOL
+    assert np.abs(out["shipped"][0] / g["mass"][:, :, :n] - 1).max() > 0.1     # the default model is a different one

@@ -109,3 +109,11 @@ def test_launcher_environment_path_without_a_gpu(tmp_path):
     r = subprocess.run([str(host.HOST_EXE), str(ini)], capture_output=True, text=True, timeout=60,
                        env={**env, "GH_RANK": "0", "GH_NRANKS": "2", "GH_UNIQUE_ID_FILE": str(tmp_path / "id")})
     assert r.returncode != 0 and "Fatal" in r.stderr
+
+
+def test_user_defined_hooks_are_tabulated_for_the_device(parsed):
+    """host/user_defined.c (the reference's src/user_defined.c:27-35): cosmo_set samples both hooks at z_arr_r2z and
+    hotpath.c hands the samples across the C-ABI."""
+    z = parsed["z_arr_r2z"]
+    assert np.allclose(parsed["frac_HI_arr"], 0.008 * (1 + z) ** 0.6, rtol=1e-14)
+    assert np.allclose(parsed["bias_HI_arr"], 0.904 + 0.135 * (1 + z) ** 1.696, rtol=1e-14)

@@ -190,3 +190,24 @@ def test_philox_stream_is_slab_independent_and_has_the_right_power(oracle, golde
     # velocity potential = delta_k f0 H0 / k^2 from the float-rounded delta_k (src/fourier.c:298)
     fac = p.fgrowth_0 * p.hubble_0
     assert np.allclose(full_v[sel], full_d[sel] * fac / k2[sel], rtol=2e-7)
+
+
+def test_user_defined_hooks_follow_an_edit(oracle):
+    """src/user_defined.c:27-35 is a file GetHI users are told to edit.  tests/golden/ref_n32_userdef.npz comes from
+    the reference compiled with oracle/userdef_variant.c in its place; the oracle, given the variant's five numbers,
+    reproduces that build's get_HI bit for bit, and with the shipped numbers it does not."""
+    from conftest import GOLDEN
+    g = dict(np.load(GOLDEN / "ref_n32_userdef.npz"))
+    p = params_of(g)
+    zz = g["probe_z"]
+    try:
+        oracle.set_user_defined(*g["userdef"])
+        assert np.array_equal(np.array([oracle.lib.oracle_bias_HI(z) for z in zz]), g["probe_bias"])
+        assert np.array_equal(np.array([oracle.lib.oracle_fraction_HI(z) for z in zz]), g["probe_frac"])
+        mass, dz = oracle.get_HI(p, float(g["sigma2_gauss"]), g["dens"], g["rvel"])
+        assert np.array_equal(mass[:, :, :32], g["mass"][:, :, :32])
+        assert np.array_equal(dz[:, :, :32], g["dz_rsd"][:, :, :32])
+    finally:
+        oracle.set_user_defined()
+    mass0, _ = oracle.get_HI(p, float(g["sigma2_gauss"]), g["dens"], g["rvel"])
+    assert np.abs(mass0[:, :, :32] / g["mass"][:, :, :32] - 1).max() > 0.1

@@ -1,4 +1,4 @@
-"""CPU check of the arithmetic behind the opt-in GH_ACC_TAYLOR variant of accumulate_kernel
+"""CPU check of the arithmetic behind the per-cell Taylor path of accumulate_kernel
 (crime_b200/csrc/gh_pixelize.cu): the per-cell second-order expansion of the two HEALPix ring coordinates,
 evaluated in float32 exactly as the kernel does and accepted only outside the cell's confidence margin, must give
 the oracle's RING pixel for every accepted sub-particle.  (The kernel itself is validated on the device by
@@ -45,23 +45,24 @@ def lean_pixels(p, centres, off):
     dr, drho = h * inv_rc, h / np.sqrt(rp2)
     e_cell = F(EPS_IDX) * fns + fns * (F(0.2123) * drho * drho * drho + F(0.375) * dr * dr * dr)
     cth_lo = F(2.0 / 3.0) - F(EPS_CTH)
-    lean = (np.abs(zh) * inv_rc + h * inv_rc < cth_lo) & ((np.abs(yh) > F(2) * h) | (xh < 0)) & (rp2 > F(576) * F(dx * dx))
-    a_lo = F(0.5) * fns + fns * F(EPS_TT) + e_cell
-    a_hi = F(4.5) * fns - fns * F(EPS_TT) - e_cell
+    # belt, far from the polar axis, and clear of the tt = 0 / 4 seam by more than the margins (kernel: `lean`)
+    lean = ((np.abs(zh) * inv_rc + dr < cth_lo) & (rp2 > F(576) * F(dx * dx)) &
+            ((xh < -h) | ((np.abs(yh) > F(2) * h) & (F(0.3) * drho * fns > fns * F(EPS_TT) + e_cell))))
     pix = np.full((len(x0), 10), -1, np.int64)
     ok_all = np.zeros((len(x0), 10), bool)
     for s in range(10):
         ox, oy, oz = F(off[s]), F(off[10 + s]), F(off[20 + s])
-        A = Ax * ox + (Ay * oy + (Axx * (ox * ox - oy * oy) + (Axy * (ox * oy) + A0)))
-        B = (Bx * ox + (By * oy + (Bz * oz + (Bxx * (ox * ox) + (Byy * (oy * oy) + (Bzz * (oz * oz) + (Bxy * (ox * oy)
-             + (Bxz * (ox * oz) + (Byz * (oy * oz) + B0)))))))))
+        # the kernel's nested evaluation (float32 sums; numpy has no fused multiply-add, which only makes this stricter)
+        A = ox * (Axy * oy + (Axx * ox + Ax)) + (oy * (-Axx * oy + Ay) + A0)
+        B = ox * (Bxz * oz + (Bxy * oy + (Bxx * ox + Bx))) + (oy * (Byz * oz + (Byy * oy + By)) + (oz * (Bzz * oz + Bz) + B0))
         a, b = A - B, A + B
         fa, fb = np.floor(a), np.floor(b)
         ra, rb = a - fa, b - fb
-        ok = (ra > e_cell) & (ra < 1 - e_cell) & (rb > e_cell) & (rb < 1 - e_cell) & (A > a_lo) & (A < a_hi) & lean
+        ok = (ra > e_cell) & (ra < 1 - e_cell) & (rb > e_cell) & (rb < 1 - e_cell) & lean
         jp, jm = fa.astype(np.int64), fb.astype(np.int64)
         ir = ns + 1 + jp - jm
-        ip = (jp + jm - ns + 2 - (ir & 1)) >> 1
+        ip = (jp + jm - ns + 1) >> 1                     # == (jp + jm - ns + kshift + 1) / 2 for either parity of ir
+        assert np.array_equal(ip[lean], ((jp + jm - ns + 2 - (ir & 1)) >> 1)[lean])
         ip = np.where(ip >= 4 * ns, ip - 4 * ns, ip)
         pix[:, s] = 2 * ns * (ns - 1) + (ir - 1) * 4 * ns + ip
         ok_all[:, s] = ok
