@@ -154,6 +154,11 @@ static int upload_tables(gh_cuda_ctx *c, const gh_cuda_params *p)
   d.z_r2z_f = df; d.gd_f = df + nz; d.gv_f = df + 2 * nz; d.nu_edges_f = df + 3 * nz; d.r_z2r_f = df + 3 * nz + nn + 1;
   d.frac_f = df + 4 * nz + nn + 1; d.bias_f = df + 5 * nz + nn + 1;
   d.inv_dz_tab = (float)(1.0 / p->dz_tab); d.z_tab_max = (float)p->z_arr_z2r[nz - 1];
+  {
+    double sv = 0;
+    for (int i = 0; i + 2 < nz; ++i) sv = fmax(sv, fabs(p->r_arr_z2r[i + 2] - 2 * p->r_arr_z2r[i + 1] + p->r_arr_z2r[i]));
+    d.rz_slope_var = (float)(1.001 * sv / p->dz_tab);
+  }
   return 0;
 }
 
@@ -524,7 +529,6 @@ extern "C" int gh_cuda_create(const gh_cuda_params *p, int rank, int nranks, con
   } while (0)
 
   CREATE_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  c->acc_taylor = getenv("GH_ACC_NO_TAYLOR") == nullptr;  // per-cell Taylor pixelisation in the equatorial belt, see accumulate_kernel
   if (getenv("GH_TIME_FFT_PASSES")) {
     for (int f = 0; f < 2; ++f)
       for (int k = 0; k < 2; ++k) CREATE_OK(cudaEventCreate(&c->ev_pass[f][k]));

@@ -37,6 +37,7 @@ struct GhDev {
   const float *nu_edges_f;  // n_nu+1 float shell edges for the fp32 fast path
   const float *r_z2r_f;     // float copy of r_arr_z2r (uniform in z, step dz_tab)
   float inv_dz_tab, z_tab_max;
+  float rz_slope_var;       // largest change of dr/dz between adjacent intervals of r_z2r_f (block shell thresholds)
   double nu_min, nu_max, inv_dnu;
   double z_lo_cull, z_hi_cull; // redshift window outside of which no sub-particle can land in a shell
   double sub_off[3 * GH_CUDA_N_SUBPART];
@@ -84,7 +85,6 @@ struct gh_cuda_ctx {
   bool have_peers;                 // peer mappings established (nranks>1, same node)
   bool time_fft_passes;            // opt-in (GH_TIME_FFT_PASSES=1): events around each field's z pass + transpose
   cudaEvent_t ev_pass[2][2];
-  bool acc_taylor;                 // per-cell Taylor pixelisation in the equatorial belt (GH_ACC_NO_TAYLOR=1 turns it off)
   bool fuse_vel;                   // gh_cuda_run*: radial velocity and get_HI in one pass
   bool sparse_reduce;              // opt-in: map reduction by pulling the peers' touched pixel intervals (GH_SPARSE_REDUCE=1)
   float *map_peers[GH_MAX_RANKS];  // every rank's accumulation stack (peer-mapped), sparse_reduce only

@@ -9,6 +9,7 @@
 // the box for the shipped frequency table).
 #include "gh_internal.cuh"
 #include "gh_index_math.cuh"
+#include "gh_group_math.cuh"
 
 namespace {
 
@@ -209,242 +210,390 @@ __device__ __forceinline__ bool fast_pixel(const FastCtx &f, float cth, float tt
   return false;
 }
 
-// One thread per cell, a warp covers 8 x 4 cells in (x, y) so that its lanes see nearly the same shells
-// and the same HEALPix regime.  Pass 1 sends each of the 10 sub-particles through the fp32 fast path: it
-// either proves the sub-particle misses every shell, or proves (shell, pixel) with all decisions clear of
-// their error bounds and deposits at once, or marks it unsure.  The azimuth is atan2 of the cell centre
-// plus the small rotation to the sub-particle (series in the tangent of the rotation angle; cells close
-// to the polar axis use atan2f per sub-particle).  Pass 2 compacts the unsure sub-particles of the CTA
-// into a shared-memory queue and re-does exactly those in fp64 (gh_point_to_shell_pixel) on as few warps
-// as possible.
-// AUDIT: nothing is deposited; every sub-particle is evaluated by both paths and the outcomes counted.
-// Planes: the launch covers gridDim.z consecutive planes; plane blockIdx.z sits at local index iz_base +
-// blockIdx.z of the buffers passed in and is global plane zg_base + blockIdx.z (this rank's own slab, or planes
-// pulled from a neighbour for load balance -- see enqueue_maps in gh_api.cu).
-// TAYLOR (default; GH_ACC_NO_TAYLOR=1 turns it off): cells whose sub-particles all lie in HEALPix's equatorial belt
-// (two thirds of the sky) get the two ring coordinates A = ns*(tt + 1/2) and B = (3/4) ns cos(theta) from a
-// second-order Taylor expansion about the cell centre.  The ten offsets are the same for every cell, so their
-// monomials are kernel-parameter constants: the loop is fully unrolled and a sub-particle costs 5 + 10 FMAs for
-// (A, B) and 4 for r^2 with constant-bank multipliers, instead of positions, rsqrt, the azimuth series and
-// cos(theta).  The third-order remainder, <= ns*(0.2123 (d/rho)^3 + 0.375 (d/r)^3) with d the half cell diagonal
-// (tools/taylor_proto.py, tests/test_taylor_pixelisation_cpu.py), is added to the confidence margin of the cell.
-// Audited on the device against the exact path at margin scales 1, 1/2, 1/4 (0 disagreements; profiles/).
-// 8 resident CTAs (64 registers): measured at 512^3 / 1024^3 the stage slows down steeply with more registers per thread
-// (99 regs: 6.3 ms, 80: 4.8, 64: 4.2 -- profiles/r2/ab_accumulate_*.log): its long prologue chains need the warps
-#ifndef GH_ACC_MIN_BLOCKS
-#define GH_ACC_MIN_BLOCKS 8
-#endif
-template <bool AUDIT, bool TAYLOR>
-__global__ void __launch_bounds__(128, GH_ACC_MIN_BLOCKS) accumulate_kernel(GhDev d, const float *__restrict__ mass,
-                                                         const float *__restrict__ dzrsd, float *__restrict__ maps,
-                                                         float eps_scale, unsigned long long *__restrict__ counts,
-                                                         int iz_base, int zg_base)
+// ---- shells of a 2 x 2 x 2 block of cells ---------------------------------------------------------------
+// The cull's redshift bracket of the block bounds which shell edges any of its sub-particles can reach (at most
+// three, else the block takes the per-cell path).  A sub-particle of a cell with Delta z_RSD = dz is beyond the
+// edge at redshift ze iff r > r_of_z(ze - dz) (z_of_r is monotone).  r_of_z is piecewise linear, so per edge the
+// block keeps r_k = r_of_z(ze_k - dz_mid) and the slope s_k of that table interval; a cell's threshold is
+// r_k - (dz - dz_mid) s_k, exact within the interval and off by at most rz_slope_var |dz - dz_mid| beyond it, which
+// goes into the cell's margin.  k = 0..2 by increasing radius, unused ones at 1e30 (never crossed).
+// j_in = shell inside the innermost edge in reach (may be outside the table: -1 or n_nu).
+struct GroupShells {
+  bool ok;
+  int j_in;
+  float r0, r1, r2, s0, s1, s2;
+};
+
+__device__ __forceinline__ void edge_radius(const FastCtx &f, float z, float &r, float &slope, bool &ok)
 {
-  __shared__ unsigned short queue[128 * GH_CUDA_N_SUBPART];
-  __shared__ float s_dz[128], s_w[128];
-  __shared__ int s_count;
-  const int ngx = 2 * d.nh;
-  const int tid = threadIdx.x + 8 * threadIdx.y;  // blockDim = (8, 16)
-  if (!AUDIT && tid == 0) s_count = 0;
-  const int ix = blockIdx.x * 8 + threadIdx.x, iy = blockIdx.y * 16 + threadIdx.y;
-  const int iz = blockIdx.z + iz_base, zg = blockIdx.z + zg_base;
-  const bool active = (ix < d.n) && (iy < d.n);
+  const float s = z * f.inv_dz;
+  const int iz = (int)s;
+  ok = ok && (z > 0.f) && (iz >= 1) && (iz < f.iz_max - 1);
+  const int i = max(0, min(iz, f.iz_max));
+  const float a = __ldg(f.rtab + i), b = __ldg(f.rtab + i + 1);
+  r = fmaf(b - a, s - (float)i, a);
+  slope = (b - a) * f.inv_dz;
+}
+
+__device__ __forceinline__ GroupShells group_shells(const FastCtx &f, float zs_lo, float zs_hi, float dz_mid)
+{
+  GroupShells g;
+  g.ok = false;
+  g.j_in = -1;
+  g.r0 = g.r1 = g.r2 = 1.0e30f;
+  g.s0 = g.s1 = g.s2 = 0.f;
+  const float nu_hi = 1420.40575177f * rcp_ftz(1.0f + zs_lo), nu_lo = 1420.40575177f * rcp_ftz(1.0f + zs_hi);
+  int j = (int)ceilf((nu_lo - f.nu_min) * f.inv_dnu);  // first edge >= nu_lo
+  j = max(0, min(j, f.n_nu));
+  for (int it = 0; it < 4 && j > 0 && __ldg(f.edges + j - 1) >= nu_lo; ++it) --j;
+  for (int it = 0; it < 4 && j <= f.n_nu && __ldg(f.edges + j) < nu_lo; ++it) ++j;
+  if (j > 0 && __ldg(f.edges + j - 1) >= nu_lo) return g;  // search did not converge (very uneven table)
+  if (j <= f.n_nu && __ldg(f.edges + j) < nu_lo) return g;
+  int ne = 0;
+  while (j + ne <= f.n_nu && __ldg(f.edges + j + ne) <= nu_hi) {
+    if (++ne > 3) return g;
+  }
+  g.j_in = j + ne - 1;  // ne == 0: the shell below edge j
+  bool ok = true;
+  if (ne > 0) edge_radius(f, 1420.40575177f * rcp_ftz(__ldg(f.edges + g.j_in)) - 1.0f - dz_mid, g.r0, g.s0, ok);
+  if (ne > 1) edge_radius(f, 1420.40575177f * rcp_ftz(__ldg(f.edges + g.j_in - 1)) - 1.0f - dz_mid, g.r1, g.s1, ok);
+  if (ne > 2) edge_radius(f, 1420.40575177f * rcp_ftz(__ldg(f.edges + g.j_in - 2)) - 1.0f - dz_mid, g.r2, g.s2, ok);
+  g.ok = ok;
+  return g;
+}
+
+// (lo, hi) thresholds on S = r^2 - |C|^2 (C = block centre, |C| = rc_hi + rc_lo) for the edge at radius r +- eps
+__device__ __forceinline__ void edge_thresholds(float r, float eps, float rc_hi, float rc_lo, float &lo, float &hi)
+{
+  const float a = fmaxf(r - eps, 0.f), b = r + eps;
+  lo = ((a - rc_hi) - rc_lo) * (a + rc_hi);
+  hi = ((b - rc_hi) - rc_lo) * (b + rc_hi);
+}
+
+struct AuditCounts {
+  unsigned long long out, in, unsure, wrong;
+};
+
+// ---- per-cell fp32 path ---------------------------------------------------------------------------------
+// For the cells the block expansion does not cover (blocks near the polar axis, astride |cos theta| = 2/3, a
+// quadrant boundary or the tt = 0 seam; a few per cent): each of the 10 sub-particles goes through the fp32 fast
+// path, which either proves it misses every shell, or proves (shell, pixel) with all decisions clear of their
+// error bounds and deposits at once, or marks it unsure (bit in the returned mask).  The azimuth is atan2 of the
+// cell centre plus the small rotation to the sub-particle (series in the tangent of the rotation angle; cells
+// close to the polar axis use atan2f per sub-particle).
+template <bool AUDIT>
+__device__ __noinline__ unsigned generic_cell(const GhDev &d, float eps_scale, double x0, double y0, double z0, float w, float dzf,
+                                              float *__restrict__ maps, AuditCounts *acp)
+{
+  // rebuilt from the (constant-bank) parameter block instead of being passed in: rarely executed, and passing them by
+  // reference would put the caller's copies on the local-memory stack
   const FastCtx f = fast_ctx_of(d, eps_scale);
   const GhIndexTables t = tables_of(d);
-  const double x0 = d.dx * (ix + 0.5) - d.pos_obs[0];
-  const double y0 = d.dx * (iy + 0.5) - d.pos_obs[1];
-  const double z0 = d.dx * (zg + 0.5) - d.pos_obs[2];
-  float dzf = 0.f, w = 0.f;
   unsigned need = 0u;
-  unsigned long long c_out = 0, c_in = 0, c_unsure = 0, c_wrong = 0;
-  if (active) {
-    const size_t idx = ((size_t)iz * d.n + iy) * ngx + ix;
-    const float cell_mass = __ldcs(mass + idx);
-    dzf = __ldcs(dzrsd + idx);
-    // cell centre as hi + lo floats: positions are xh + (xl + offset), one rounding of the full coordinate
-    const float xh = (float)x0, yh = (float)y0, zh = (float)z0;
-    const float xl = (float)(x0 - (double)xh), yl = (float)(y0 - (double)yh), zl = (float)(z0 - (double)zh);
-    const float rp2 = fmaf(xh, xh, yh * yh);
-    const float rc = sqrtf(fmaf(zh, zh, rp2));
-    // conservative cull: all sub-particles lie within half a cell diagonal of the centre and z_of_r is
-    // non-decreasing, so their redshifts lie in [z(rc-h), z(rc+h)] + dz; 1e-3 Mpc/h and 1e-5 in z cover
-    // the fp32 evaluation of this test
-    const float h = (float)d.dx * 0.8660254f + 1e-3f + 1e-6f * rc;
-    const float zs_hi = z_of_r_f(f, rc + h) + dzf + 1e-5f, zs_lo = z_of_r_f(f, rc - h) + dzf - 1e-5f;
-    const bool culled = (zs_hi < (float)d.z_lo_cull || zs_lo > (float)d.z_hi_cull);
-    if (AUDIT && culled) {
+  // cell centre as hi + lo floats: positions are xh + (xl + offset), one rounding of the full coordinate
+  const float xh = (float)x0, yh = (float)y0, zh = (float)z0;
+  const float xl = (float)(x0 - (double)xh), yl = (float)(y0 - (double)yh), zl = (float)(z0 - (double)zh);
+  const float rp2 = fmaf(xh, xh, yh * yh);
+  const float rc = sqrtf(fmaf(zh, zh, rp2));
+  // conservative cull: all sub-particles lie within half a cell diagonal of the centre and z_of_r is
+  // non-decreasing, so their redshifts lie in [z(rc-h), z(rc+h)] + dz; 1e-3 Mpc/h and 1e-5 in z cover
+  // the fp32 evaluation of this test
+  const float h = (float)d.dx * 0.8660254f + 1e-3f + 1e-6f * rc;
+  const float zs_hi = z_of_r_f(f, rc + h) + dzf + 1e-5f, zs_lo = z_of_r_f(f, rc - h) + dzf - 1e-5f;
+  const bool culled = (zs_hi < (float)d.z_lo_cull || zs_lo > (float)d.z_hi_cull);
+  if (culled) {
+    if (AUDIT) {
       for (int isub = 0; isub < GH_CUDA_N_SUBPART; ++isub) {
         long long pe;
         gh_point_to_shell_pixel(t, x0 + d.sub_off[isub], y0 + d.sub_off[GH_CUDA_N_SUBPART + isub],
                                 z0 + d.sub_off[2 * GH_CUDA_N_SUBPART + isub], (double)dzf, &pe);
-        c_out++;
-        if (pe >= 0) c_wrong++;
+        acp->out++;
+        if (pe >= 0) acp->wrong++;
+      }
+    }
+    return 0u;
+  }
+  // azimuth of the cell centre; sub-particles rotate it by atan(cross/dot), |cross/dot| < 0.05 when
+  // the cell is further than 24 cells from the polar axis
+  const bool series = rp2 > 576.0f * (float)(d.dx * d.dx);
+  const float phi_c = atan2f(yh, xh);
+  const CellShells cs = cell_shells(f, zs_lo, zs_hi, dzf);
+#pragma unroll 2
+  for (int isub = 0; isub < GH_CUDA_N_SUBPART; ++isub) {
+    const float ox = xl + d.sub_off_f[isub], oy = yl + d.sub_off_f[GH_CUDA_N_SUBPART + isub];
+    const float x = xh + ox, y = yh + oy, z = zh + (zl + d.sub_off_f[2 * GH_CUDA_N_SUBPART + isub]);
+    const float q = fmaf(x, x, y * y);
+    const float r2 = fmaf(z, z, q);
+    const float inv_r = rsqrt_ftz(r2);
+    int inu, pix = -1, st;
+    if (cs.ok) {
+      // two comparisons of r^2 against the cell's shell-edge radii
+      const bool in0 = r2 < cs.lo_a, in1 = (r2 > cs.hi_a) & (r2 < cs.lo_b), in2 = r2 > cs.hi_b;
+      inu = in0 ? cs.shell[0] : (in1 ? cs.shell[1] : cs.shell[2]);
+      st = (in0 | in1 | in2) ? (inu >= 0 ? GH_FAST_IN : GH_FAST_OUT) : GH_FAST_UNSURE;
+    } else {
+      const float nu = 1420.40575177f * rcp_ftz(1.0f + (z_of_r_f(f, r2 * inv_r) + dzf));
+      st = fast_shell(f, nu, inu);
+    }
+    if (st == GH_FAST_IN) {
+      float phi;
+      if (series) {
+        const float tq = fmaf(xh, oy, -yh * ox) * rcp_ftz(rp2 + fmaf(xh, ox, yh * oy));
+        const float t2 = tq * tq;
+        phi = fmaf(tq, fmaf(t2, fmaf(t2, 0.2f, -0.33333333f), 1.0f), phi_c);
+      } else {
+        phi = atan2f(y, x);
+      }
+      float tt = phi * 0.63661977236758134308f;
+      tt += (tt < 0.f) ? 4.0f : 0.f;
+      if (!fast_pixel(f, z * inv_r, tt, q, inv_r, pix)) st = GH_FAST_UNSURE;
+    }
+    if (!AUDIT) {
+      if (st == GH_FAST_IN) atomicAdd(maps + ((size_t)d.npix * inu + pix), w);
+      else if (st == GH_FAST_UNSURE) need |= 1u << isub;
+    } else {
+      long long pe;
+      const int se = gh_point_to_shell_pixel(t, x0 + d.sub_off[isub], y0 + d.sub_off[GH_CUDA_N_SUBPART + isub],
+                                             z0 + d.sub_off[2 * GH_CUDA_N_SUBPART + isub], (double)dzf, &pe);
+      if (st == GH_FAST_OUT) { acp->out++; if (pe >= 0) acp->wrong++; }
+      else if (st == GH_FAST_IN) { acp->in++; if (inu != se || (long long)pix != pe) acp->wrong++; }
+      else acp->unsure++;
+    }
+  }
+  return need;
+}
+
+// ---- accumulate_kernel ------------------------------------------------------------------------------------
+// One thread per 2 x 2 x 2 block of cells; a CTA of 16 x 8 threads covers 32 x 16 cells of a pair of planes, a warp
+// 32 x 4 x 2 cells, so that its lanes see nearly the same shells and the same HEALPix regime.
+//   1. Block cull: every sub-particle lies within sqrt(3) dx of the block centre and z_of_r is monotone, so their
+//      redshifts lie in [z(r_C - hg) + min dz, z(r_C + hg) + max dz]; blocks whose bracket misses the shells'
+//      redshift window are skipped (about 44 % of the box for the shipped frequency table).
+//   2. Block expansion (gh_group_math.cuh): the two pixel coordinates and r^2 to second order about the block
+//      centre, once per block; per cell the expansion point is shifted to the cell centre (exact for quadratics)
+//      and the shell edges in reach become thresholds on r^2; per sub-particle 18 FMAs with constant offsets,
+//      the 1.5 * 2^23 rounding trick instead of floor(), a handful of integer operations and one RED.
+//   3. Cells the expansion does not cover (a few per cent, but one in most warps) are queued in shared memory and
+//      taken through the per-cell fp32 path above by all threads of the CTA afterwards -- run in place they would
+//      hold the whole warp for a thousand instructions each.
+//   4. Sub-particles that either fast path calls unsure (a rounding decision closer to its boundary than the
+//      error bound) are queued likewise and re-done in IEEE double with the exact restatement of the reference's
+//      arithmetic (gh_point_to_shell_pixel).
+// Accepted fast answers equal the exact path's by construction; AUDIT (gh_cuda_accumulate_audit) measures that on
+// the device: nothing is deposited, every sub-particle is evaluated by both paths and the outcomes are counted,
+// also with the error bounds scaled down.
+// Planes: the launch covers `nplanes` consecutive planes in pairs; plane k sits at local index iz_base + k of the
+// buffers passed in and is global plane zg_base + k (this rank's own slab, or planes pulled from a neighbour for
+// load balance -- see enqueue_maps in gh_api.cu).  An odd last plane is a block with four cells.
+#ifndef GH_ACC_MIN_BLOCKS
+#define GH_ACC_MIN_BLOCKS 7
+#endif
+#define GH_ACC_QCAP (128 * 8 * GH_CUDA_N_SUBPART)
+#ifndef GH_ACC_SUB_UNROLL
+#define GH_ACC_SUB_UNROLL 2
+#endif
+constexpr int kAccSubUnroll = GH_ACC_SUB_UNROLL;  // #pragma unroll takes a constant expression, not a macro
+
+template <bool AUDIT>
+__global__ void __launch_bounds__(128, GH_ACC_MIN_BLOCKS) accumulate_kernel(const __grid_constant__ GhDev d, const float *__restrict__ mass,
+                                                         const float *__restrict__ dzrsd, float *__restrict__ maps,
+                                                         float eps_scale, unsigned long long *__restrict__ counts,
+                                                         int iz_base, int zg_base, int nplanes)
+{
+  __shared__ unsigned short xqueue[GH_ACC_QCAP];  // unsure sub-particles: tid << 7 | cell << 4 | sub-particle
+  __shared__ unsigned short cqueue[128 * 8];      // cells for the per-cell path: tid << 3 | cell
+  __shared__ float s_w[8][128], s_dz[8][128];
+  __shared__ int s_nx, s_nc;
+  const int ngx = 2 * d.nh;
+  const int tid = threadIdx.x + 16 * threadIdx.y;  // blockDim = (16, 8)
+  if (tid == 0) { s_nx = 0; s_nc = 0; }
+  const int cx = 2 * (blockIdx.x * 16 + threadIdx.x), cy = 2 * (blockIdx.y * 8 + threadIdx.y);  // first cell of the block
+  const int pz0 = 2 * blockIdx.z;
+  const int nzv = min(2, nplanes - pz0);
+  const int zg = zg_base + pz0;
+  const bool active = (cx < d.n) && (cy < d.n);
+  const unsigned valid = active ? (nzv == 2 ? 0xFFu : 0x0Fu) : 0u;
+  AuditCounts ac = {0, 0, 0, 0};
+  float dz_min = 3.0e38f, dz_max = -3.0e38f;
+#pragma unroll
+  for (int pz = 0; pz < 2; ++pz) {
+#pragma unroll
+    for (int py = 0; py < 2; ++py) {
+      float2 m = make_float2(0.f, 0.f), z = make_float2(0.f, 0.f);
+      if (active && pz < nzv) {
+        const size_t idx = ((size_t)(iz_base + pz0 + pz) * d.n + (cy + py)) * ngx + cx;
+        m = __ldcs(reinterpret_cast<const float2 *>(mass + idx));
+        z = __ldcs(reinterpret_cast<const float2 *>(dzrsd + idx));
+        dz_min = fminf(dz_min, fminf(z.x, z.y));
+        dz_max = fmaxf(dz_max, fmaxf(z.x, z.y));
+      }
+      const int c = pz * 4 + py * 2;
+      // src/pixelize.c:203: float / int is a float division in C
+      s_w[c][tid] = __fdiv_rn(m.x, (float)GH_CUDA_N_SUBPART);
+      s_w[c + 1][tid] = __fdiv_rn(m.y, (float)GH_CUDA_N_SUBPART);
+      s_dz[c][tid] = z.x;
+      s_dz[c + 1][tid] = z.y;
+    }
+  }
+  __syncthreads();  // the queue counters
+  if (active) {
+    const FastCtx f = fast_ctx_of(d, eps_scale);
+    // block centre (exact, double)
+    const double X = d.dx * (cx + 1.0) - d.pos_obs[0], Y = d.dx * (cy + 1.0) - d.pos_obs[1], Z = d.dx * (zg + 1.0) - d.pos_obs[2];
+    const float xh = (float)X, yh = (float)Y, zh = (float)Z;
+    const float rc = sqrtf(fmaf(zh, zh, fmaf(xh, xh, yh * yh)));
+    const float hg = (float)d.dx * 1.7320508f + 1e-3f + 1e-6f * rc;
+    const float zs_hi = z_of_r_f(f, rc + hg) + dz_max + 1e-5f, zs_lo = z_of_r_f(f, rc - hg) + dz_min - 1e-5f;
+    const bool culled = (zs_hi < (float)d.z_lo_cull || zs_lo > (float)d.z_hi_cull);
+    if (AUDIT && culled) {
+      const GhIndexTables t = tables_of(d);
+      for (int c = 0; c < 8; ++c) {
+        if (!((valid >> c) & 1u)) continue;
+        const double x0 = d.dx * (cx + (c & 1) + 0.5) - d.pos_obs[0], y0 = d.dx * (cy + ((c >> 1) & 1) + 0.5) - d.pos_obs[1];
+        const double z0 = d.dx * (zg + (c >> 2) + 0.5) - d.pos_obs[2];
+        for (int isub = 0; isub < GH_CUDA_N_SUBPART; ++isub) {
+          long long pe;
+          gh_point_to_shell_pixel(t, x0 + d.sub_off[isub], y0 + d.sub_off[GH_CUDA_N_SUBPART + isub],
+                                  z0 + d.sub_off[2 * GH_CUDA_N_SUBPART + isub], (double)s_dz[c][tid], &pe);
+          ac.out++;
+          if (pe >= 0) ac.wrong++;
+        }
       }
     }
     if (!culled) {
-      w = __fdiv_rn(cell_mass, (float)GH_CUDA_N_SUBPART);  // src/pixelize.c:203: float / int is a float division in C
-      // azimuth of the cell centre; sub-particles rotate it by atan(cross/dot), |cross/dot| < 0.05 when
-      // the cell is further than 24 cells from the polar axis
-      const bool series = rp2 > 576.0f * (float)(d.dx * d.dx);
-      const float phi_c = atan2f(yh, xh);
-      const CellShells cs = cell_shells(f, zs_lo, zs_hi, dzf);
-      bool lean = false;
-      if constexpr (TAYLOR) {
-        const float inv_rc = rsqrt_ftz(fmaf(zh, zh, rp2)), inv_rho = rsqrt_ftz(rp2);
-        // third-order remainder of both expansions (h = half cell diagonal + slack), on top of the fp32 margin
-        const float fns = f.fns, dr = h * inv_rc, drho = h * inv_rho;
-        const float e_cell = f.eidx + fns * fmaf(0.2123f * drho, drho * drho, 0.375f * dr * dr * dr);
-        // every sub-particle of the cell in the equatorial belt (|d cos(theta)| <= d/r), the cell's shells known as
-        // r^2 thresholds, and every sub-particle's azimuth clear of the tt = 0 / 4 seam by more than the margins
-        // (|y| > h for all of them when x > 0, so tt and 4 - tt exceed (2/pi) atan(h/(rho+h)) > 0.3 h/rho)
-        lean = cs.ok && series && (fabsf(zh) * inv_rc + dr < f.cth_lo) &&
-               (xh < -h || (fabsf(yh) > 2.0f * h && 0.3f * drho * fns > fns * f.eps_tt + e_cell));
-        if (lean) {
-          const float irho2 = inv_rho * inv_rho, ir2 = inv_rc * inv_rc, ir3 = inv_rc * ir2, ir5 = ir3 * ir2;
-          const float k = 0.63661977236758134308f * fns, kq = k * irho2 * irho2, c34 = 0.75f * fns;
-          float ttc = phi_c * 0.63661977236758134308f;
-          ttc += (ttc < 0.f) ? 4.0f : 0.f;
-          // A = A0 + Ax ox + Ay oy + Axx (ox^2 - oy^2) + Axy ox oy, evaluated as A0 + oy (Ay - Axx oy) + ox (Ax + Axx ox + Axy oy)
-          const float Ax = -k * yh * irho2, Ay = k * xh * irho2;
-          const float Axx = kq * xh * yh, nAxx = -Axx, Axy = kq * fmaf(yh, yh, -xh * xh);
-          const float A0 = fmaf(Ax, xl, fmaf(Ay, yl, fmaf(fns, ttc, 0.5f * fns)));
-          // B = B0 + oz (Bz + Bzz oz) + oy (By + Byy oy + Byz oz) + ox (Bx + Bxx ox + Bxy oy + Bxz oz)
-          const float zi3 = zh * ir3, t3 = 3.0f * zh * ir5;
-          const float Bx = -c34 * xh * zi3, By = -c34 * yh * zi3, Bz = c34 * rp2 * ir3;
-          const float Bxx = 0.5f * c34 * fmaf(t3 * xh, xh, -zi3), Byy = 0.5f * c34 * fmaf(t3 * yh, yh, -zi3);
-          const float Bzz = 0.5f * c34 * fmaf(t3 * zh, zh, -3.0f * zi3);
-          const float Bxy = c34 * t3 * xh * yh, Bxz = c34 * fmaf(t3 * xh, zh, -xh * ir3), Byz = c34 * fmaf(t3 * yh, zh, -yh * ir3);
-          const float B0 = fmaf(Bx, xl, fmaf(By, yl, fmaf(Bz, zl, c34 * zh * inv_rc)));
-          const float r2c = fmaf(2.0f * xh, xl, fmaf(2.0f * yh, yl, fmaf(2.0f * zh, zl, fmaf(zh, zh, rp2))));
-          const float x2 = 2.0f * xh, y2 = 2.0f * yh, z2 = 2.0f * zh;
-          const float m_lo = e_cell, m_hi = 1.0f - e_cell;
-          const int ns = f.ns, ns4 = 4 * ns, n_nu = f.n_nu, j_in = cs.j_in, npix32 = (int)d.npix;
-          int pix0 = 2 * ns * (ns - 1) + ns * ns4;                // pix = pix0 + (jp - jm) * 4 ns + ip
-          const float lo_a = cs.lo_a, hi_a = cs.hi_a, lo_b = cs.lo_b, hi_b = cs.hi_b;
-          // global address of shell j_in's map (never dereferenced out of range).  Opaque to the optimiser from here on:
-          // otherwise it folds base and pix0 back into every sub-particle's address arithmetic (a 64-bit multiply and two
-          // more integer operations per deposit) instead of keeping them in registers
-          unsigned long long shell_base = (unsigned long long)__cvta_generic_to_global(maps) + 4ull * (unsigned long long)((long long)d.npix * j_in);
-          asm volatile("" : "+l"(shell_base), "+r"(pix0));
-          // fully unrolled: the ten offsets (x, y, z, |o|^2) are kernel-parameter constants, one 16-byte uniform load each
-#pragma unroll
+      const float dz_mid = 0.5f * (dz_min + dz_max);
+      const GroupShells gs = group_shells(f, zs_lo, zs_hi, dz_mid);
+      GhGroupExp g;
+      g.kind = GH_GRP_NONE;
+      g.rc = 0.0;
+      g.e = 0.f;
+      if (gs.ok) gh_group_expand(X, Y, Z, hg, f.fns, eps_scale, g);
+      if (g.kind == GH_GRP_NONE) {
+        // the whole block goes to the per-cell path
+        int at = atomicAdd(&s_nc, __popc(valid));
+        for (int c = 0; c < 8; ++c)
+          if ((valid >> c) & 1u) cqueue[at++] = (unsigned short)((tid << 3) | c);
+      } else {
+        const float rc_hi = (float)g.rc, rc_lo = (float)(g.rc - (double)rc_hi);
+        const float hm = 0.5f - g.e;
+        const float hdx = (float)(0.5 * d.dx);
+        const int ns = f.ns, n_nu = f.n_nu, npix32 = (int)d.npix, j0 = gs.j_in;
+        const bool polar = g.kind != GH_GRP_EQ;
+        // equatorial: pix = k_b + (jp - jm) k_a + ip; polar: pix = ir (k_a ir + k_b) + ip_f + k_c (gh_group_math.cuh)
+        int k_a, k_b, k_c;
+        if (!polar) {
+          k_a = 4 * ns;
+          k_b = 2 * ns * (ns - 1) + ns * 4 * ns;
+          k_c = (int)(2u * (unsigned)g.kbase - (unsigned)ns + 1u - 2u * (unsigned)GH_GRP_MAGIC_BITS);
+        } else {
+          k_a = (g.kind == GH_GRP_SOUTH) ? -2 : 2;
+          k_b = g.kbase - 2;
+          k_c = (int)((g.kind == GH_GRP_SOUTH ? (unsigned)npix32 : 0u) - (unsigned)GH_GRP_MAGIC_BITS);
+        }
+        // global address of shell j0's map (never dereferenced out of range).  Opaque to the optimiser from here on:
+        // otherwise it folds the 64-bit base arithmetic back into every sub-particle's address
+        unsigned long long shell_base =
+            (unsigned long long)__cvta_generic_to_global(maps) + 4ull * (unsigned long long)((long long)d.npix * j0);
+        int npix_neg = -npix32;
+        asm volatile("" : "+l"(shell_base), "+r"(npix_neg));
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          if (!((valid >> c) & 1u)) continue;
+          const float w = s_w[c][tid], dzc = s_dz[c][tid];
+          GhCellExp ce;
+          gh_group_recentre(g, (c & 1) ? hdx : -hdx, (c & 2) ? hdx : -hdx, (c & 4) ? hdx : -hdx, ce);
+          // shell thresholds of this cell: the block's edge radii shifted by its own Delta z_RSD
+          const float ddz = dzc - dz_mid;
+          const float eps = fmaf(d.rz_slope_var, fabsf(ddz), f.eps_r);
+          float lo_a, hi_a, lo_b, hi_b, lo_c, hi_c;
+          edge_thresholds(fmaf(-ddz, gs.s0, gs.r0), eps, rc_hi, rc_lo, lo_a, hi_a);
+          edge_thresholds(fmaf(-ddz, gs.s1, gs.r1), eps, rc_hi, rc_lo, lo_b, hi_b);
+          edge_thresholds(fmaf(-ddz, gs.s2, gs.r2), eps, rc_hi, rc_lo, lo_c, hi_c);
+          unsigned need = 0u;
+#pragma unroll kAccSubUnroll
           for (int isub = 0; isub < GH_CUDA_N_SUBPART; ++isub) {
             const float4 o = d.sub_c[isub];
-            const float r2 = fmaf(x2, o.x, fmaf(y2, o.y, fmaf(z2, o.z, r2c + o.w)));
-            // shell: j_in inside the inner edge, one less beyond each edge crossed; unsure within eps_r of an edge
-            const bool p1 = r2 > hi_a, p2 = r2 > hi_b;
-            const bool sure = ((r2 < lo_a) || p1) && ((r2 < lo_b) || p2);
-            const int inu = j_in - (p1 ? 1 : 0) - (p2 ? 1 : 0);
-            const bool inside = (unsigned)inu < (unsigned)n_nu;
-            const float A = fmaf(o.x, fmaf(Axy, o.y, fmaf(Axx, o.x, Ax)), fmaf(o.y, fmaf(nAxx, o.y, Ay), A0));
-            const float B = fmaf(o.x, fmaf(Bxz, o.z, fmaf(Bxy, o.y, fmaf(Bxx, o.x, Bx))),
-                                 fmaf(o.y, fmaf(Byz, o.z, fmaf(Byy, o.y, By)), fmaf(o.z, fmaf(Bzz, o.z, Bz), B0)));
-            const float a = A - B, b = A + B;
-            const float fa = floorf(a), fb = floorf(b);
-            const float ra = a - fa, rb = b - fb;
-            const bool ok = (ra > m_lo) && (ra < m_hi) && (rb > m_lo) && (rb < m_hi);
-            const int jp = (int)fa, jm = (int)fb;
-            // ir - 1 = ns + jp - jm;  ip = (jp + jm - ns + kshift + 1) / 2 with kshift = 1 - (ir & 1): jp + jm - ns + 1
-            // has the parity of ir, so the division is (jp + jm - ns + 1) >> 1 for either parity
-            int ip = (jp + jm - ns + 1) >> 1;
-            ip -= (ip >= ns4) ? ns4 : 0;
-            const int pix = pix0 + (jp - jm) * ns4 + ip;
+            const float S = gh_cell_S(ce, o.x, o.y, o.z, o.w);
+            // shell: j0 inside the innermost edge, one less beyond each edge crossed; unsure within eps of an edge
+            const bool p1 = S > hi_a, p2 = S > hi_b, p3 = S > hi_c;
+            const bool sure = ((S < lo_a) || p1) && ((S < lo_b) || p2) && ((S < lo_c) || p3);
+            const int dj = (p1 ? 1 : 0) + (p2 ? 1 : 0) + (p3 ? 1 : 0);
+            const bool inside = (unsigned)(j0 - dj) < (unsigned)n_nu;
+            const float U = gh_cell_U(g, ce, o.x, o.y), V = gh_cell_V(g, ce, o.x, o.y, o.z);
+            int pix;
+            const bool ok = polar ? gh_sub_polar(U, V, hm, k_a, k_b, k_c, pix) : gh_sub_eq(U, V, hm, k_a, k_b, k_c, pix);
             if (!AUDIT) {
               if (sure && inside && ok) {
-                const int rel = pix - (p1 ? npix32 : 0) - (p2 ? npix32 : 0);
+                const int rel = dj * npix_neg + pix;
                 asm volatile("red.global.add.f32 [%0], %1;" ::"l"(shell_base + 4ll * (long long)rel), "f"(w));
+              } else if (!sure || inside) {
+                need |= 1u << isub;  // sure && !inside: surely outside every shell
               }
-              else if (!sure || inside) need |= 1u << isub;  // sure && !inside: surely outside every shell
             } else {
+              const GhIndexTables t = tables_of(d);
+              const double x0 = d.dx * (cx + (c & 1) + 0.5) - d.pos_obs[0], y0 = d.dx * (cy + ((c >> 1) & 1) + 0.5) - d.pos_obs[1];
+              const double z0 = d.dx * (zg + (c >> 2) + 0.5) - d.pos_obs[2];
               long long pe;
               const int se = gh_point_to_shell_pixel(t, x0 + d.sub_off[isub], y0 + d.sub_off[GH_CUDA_N_SUBPART + isub],
-                                                     z0 + d.sub_off[2 * GH_CUDA_N_SUBPART + isub], (double)dzf, &pe);
-              if (sure && !inside) { c_out++; if (pe >= 0) c_wrong++; }
-              else if (sure && ok) { c_in++; if (inu != se || (long long)pix != pe) c_wrong++; }
-              else c_unsure++;
+                                                     z0 + d.sub_off[2 * GH_CUDA_N_SUBPART + isub], (double)dzc, &pe);
+              if (sure && !inside) { ac.out++; if (pe >= 0) ac.wrong++; }
+              else if (sure && ok) { ac.in++; if (j0 - dj != se || (long long)pix != pe) ac.wrong++; }
+              else ac.unsure++;
+            }
+          }
+          if (!AUDIT && need) {
+            int at = atomicAdd(&s_nx, __popc(need));
+            while (need) {
+              const int isub = __ffs(need) - 1;
+              need &= need - 1;
+              xqueue[at++] = (unsigned short)((tid << 7) | (c << 4) | isub);
             }
           }
         }
       }
-      if (!lean) {
-#pragma unroll 2
-      for (int isub = 0; isub < GH_CUDA_N_SUBPART; ++isub) {
-        const float ox = xl + d.sub_off_f[isub], oy = yl + d.sub_off_f[GH_CUDA_N_SUBPART + isub];
-        const float x = xh + ox, y = yh + oy, z = zh + (zl + d.sub_off_f[2 * GH_CUDA_N_SUBPART + isub]);
-        const float q = fmaf(x, x, y * y);
-        const float r2 = fmaf(z, z, q);
-        const float inv_r = rsqrt_ftz(r2);
-        int inu, pix = -1, st;
-        if (cs.ok) {
-          // two comparisons of r^2 against the cell's shell-edge radii
-          const bool in0 = r2 < cs.lo_a, in1 = (r2 > cs.hi_a) & (r2 < cs.lo_b), in2 = r2 > cs.hi_b;
-          inu = in0 ? cs.shell[0] : (in1 ? cs.shell[1] : cs.shell[2]);
-          st = (in0 | in1 | in2) ? (inu >= 0 ? GH_FAST_IN : GH_FAST_OUT) : GH_FAST_UNSURE;
-        } else {
-          const float nu = 1420.40575177f * rcp_ftz(1.0f + (z_of_r_f(f, r2 * inv_r) + dzf));
-          st = fast_shell(f, nu, inu);
-        }
-        if (st == GH_FAST_IN) {
-          float phi;
-          if (series) {
-            const float tq = fmaf(xh, oy, -yh * ox) * rcp_ftz(rp2 + fmaf(xh, ox, yh * oy));
-            const float t2 = tq * tq;
-            phi = fmaf(tq, fmaf(t2, fmaf(t2, 0.2f, -0.33333333f), 1.0f), phi_c);
-          } else {
-            phi = atan2f(y, x);
-          }
-          float tt = phi * 0.63661977236758134308f;
-          tt += (tt < 0.f) ? 4.0f : 0.f;
-          if (!fast_pixel(f, z * inv_r, tt, q, inv_r, pix)) st = GH_FAST_UNSURE;
-        }
-        if (!AUDIT) {
-          if (st == GH_FAST_IN) atomicAdd(maps + ((size_t)d.npix * inu + pix), w);
-          else if (st == GH_FAST_UNSURE) need |= 1u << isub;
-        } else {
-          long long pe;
-          const int se = gh_point_to_shell_pixel(t, x0 + d.sub_off[isub], y0 + d.sub_off[GH_CUDA_N_SUBPART + isub],
-                                                 z0 + d.sub_off[2 * GH_CUDA_N_SUBPART + isub], (double)dzf, &pe);
-          if (st == GH_FAST_OUT) { c_out++; if (pe >= 0) c_wrong++; }
-          else if (st == GH_FAST_IN) { c_in++; if (inu != se || (long long)pix != pe) c_wrong++; }
-          else c_unsure++;
-        }
-      }
+    }
+  }
+  // ---- per-cell path for the queued cells, all threads ----
+  __syncthreads();
+  const int ncells = s_nc;
+  for (int j = tid; j < ncells; j += 128) {
+    const unsigned e = cqueue[j];
+    const int src = e >> 3, c = e & 7;
+    const int sx = 2 * (blockIdx.x * 16 + (src & 15)) + (c & 1), sy = 2 * (blockIdx.y * 8 + (src >> 4)) + ((c >> 1) & 1);
+    const double x0 = d.dx * (sx + 0.5) - d.pos_obs[0], y0 = d.dx * (sy + 0.5) - d.pos_obs[1];
+    const double z0 = d.dx * (zg + (c >> 2) + 0.5) - d.pos_obs[2];
+    unsigned need = generic_cell<AUDIT>(d, eps_scale, x0, y0, z0, s_w[c][src], s_dz[c][src], maps, AUDIT ? &ac : nullptr);
+    if (!AUDIT && need) {
+      int at = atomicAdd(&s_nx, __popc(need));
+      while (need) {
+        const int isub = __ffs(need) - 1;
+        need &= need - 1;
+        xqueue[at++] = (unsigned short)((src << 7) | (c << 4) | isub);
       }
     }
   }
   if (AUDIT) {
-    atomicAdd(counts + 0, c_out);
-    atomicAdd(counts + 1, c_in);
-    atomicAdd(counts + 2, c_unsure);
-    atomicAdd(counts + 3, c_wrong);
+    atomicAdd(counts + 0, ac.out);
+    atomicAdd(counts + 1, ac.in);
+    atomicAdd(counts + 2, ac.unsure);
+    atomicAdd(counts + 3, ac.wrong);
     return;
   }
-  // ---- pass 2: exact path for the unsure sub-particles of this CTA ----
-  // (a few per CTA: they are compacted into one queue so that a single warp runs the expensive fp64 code)
-  s_dz[tid] = dzf;
-  s_w[tid] = w;
-  __syncthreads();  // s_count = 0 visible; also orders the s_dz / s_w writes
-  if (need) {
-    int at = atomicAdd(&s_count, __popc(need));
-    unsigned m = need;
-    while (m) {
-      const int isub = __ffs(m) - 1;
-      m &= m - 1;
-      queue[at++] = (unsigned short)((tid << 4) | isub);
-    }
-  }
+  // ---- exact path for the unsure sub-particles of this CTA ----
   __syncthreads();
-  const int total = s_count;
+  const int total = s_nx;
+  if (total == 0) return;
+  const GhIndexTables t = tables_of(d);
   for (int j = tid; j < total; j += 128) {
-    const unsigned e = queue[j];
-    const int src = e >> 4, isub = e & 15;
-    const int sx = blockIdx.x * 8 + (src & 7), sy = blockIdx.y * 16 + (src >> 3);
+    const unsigned e = xqueue[j];
+    const int src = e >> 7, c = (e >> 4) & 7, isub = e & 15;
+    const int sx = 2 * (blockIdx.x * 16 + (src & 15)) + (c & 1), sy = 2 * (blockIdx.y * 8 + (src >> 4)) + ((c >> 1) & 1);
     const double px = d.dx * (sx + 0.5) - d.pos_obs[0] + d.sub_off[isub];
     const double py = d.dx * (sy + 0.5) - d.pos_obs[1] + d.sub_off[GH_CUDA_N_SUBPART + isub];
+    const double pz = d.dx * (zg + (c >> 2) + 0.5) - d.pos_obs[2] + d.sub_off[2 * GH_CUDA_N_SUBPART + isub];
     long long ipix;
-    const double pz = d.dx * (zg + 0.5) - d.pos_obs[2] + d.sub_off[2 * GH_CUDA_N_SUBPART + isub];  // z0 again: nothing of the prologue stays live
-    const int inu = gh_point_to_shell_pixel(t, px, py, pz, (double)s_dz[src], &ipix);
-    if (ipix >= 0) atomicAdd(maps + (size_t)ipix + (size_t)d.npix * inu, s_w[src]);
+    const int inu = gh_point_to_shell_pixel(t, px, py, pz, (double)s_dz[c][src], &ipix);
+    if (ipix >= 0) atomicAdd(maps + (size_t)ipix + (size_t)d.npix * inu, s_w[c][src]);
   }
 }
 
@@ -596,9 +745,8 @@ int gh_launch_accumulate(gh_cuda_ctx *c, const float *mass, const float *dzrsd, 
 {
   const GhDev &d = c->d;
   if (nplanes <= 0) return 0;
-  dim3 grid((d.n + 7) / 8, (d.n + 15) / 16, nplanes), block(8, 16);
-  if (c->acc_taylor) accumulate_kernel<false, true><<<grid, block, 0, c->stream>>>(d, mass, dzrsd, c->maps, 1.0f, nullptr, iz_base, zg_base);
-  else accumulate_kernel<false, false><<<grid, block, 0, c->stream>>>(d, mass, dzrsd, c->maps, 1.0f, nullptr, iz_base, zg_base);
+  dim3 grid((d.n + 31) / 32, (d.n + 15) / 16, (nplanes + 1) / 2), block(16, 8);
+  accumulate_kernel<false><<<grid, block, 0, c->stream>>>(d, mass, dzrsd, c->maps, 1.0f, nullptr, iz_base, zg_base, nplanes);
   GH_LAUNCH_CHECK(c);
   return 0;
 }
@@ -606,10 +754,9 @@ int gh_launch_accumulate(gh_cuda_ctx *c, const float *mass, const float *dzrsd, 
 int gh_launch_accumulate_audit(gh_cuda_ctx *c, float eps_scale, unsigned long long *d_counts)
 {
   const GhDev &d = c->d;
-  dim3 grid((d.n + 7) / 8, (d.n + 15) / 16, d.nz_here), block(8, 16);
+  dim3 grid((d.n + 31) / 32, (d.n + 15) / 16, (d.nz_here + 1) / 2), block(16, 8);
   const float *m = reinterpret_cast<const float *>(c->gridA), *z = reinterpret_cast<const float *>(c->gridC);
-  if (c->acc_taylor) accumulate_kernel<true, true><<<grid, block, 0, c->stream>>>(d, m, z, c->maps, eps_scale, d_counts, 0, d.iz0);
-  else accumulate_kernel<true, false><<<grid, block, 0, c->stream>>>(d, m, z, c->maps, eps_scale, d_counts, 0, d.iz0);
+  accumulate_kernel<true><<<grid, block, 0, c->stream>>>(d, m, z, c->maps, eps_scale, d_counts, 0, d.iz0, d.nz_here);
   GH_LAUNCH_CHECK(c);
   return 0;
 }

@@ -526,21 +526,54 @@ def test_full_size_properties_512(tables_nu64):
         assert np.abs(a2[nz] / (2.0 * a1[nz]) - 1).max() < 1e-5
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("GH_TEST_EXPERIMENTAL"), reason="opt-in variants not yet validated on hardware")
-def test_experimental_taylor_pixelisation_audit(tables_nu64):
-    """GH_ACC_TAYLOR=1 (per-cell Taylor expansion of the ring coordinates in the equatorial belt): the on-device
-    audit must find no disagreement with the exact path, also with the margins halved.  Run with
-    GH_TEST_EXPERIMENTAL=1 GH_ACC_TAYLOR=1; not part of the default suite until it has been."""
-    import os
+@pytest.mark.parametrize("n_grid,n_side", [(256, 256), (512, 256)])
+def test_block_expansion_audit_with_scaled_margins(tables_nu64, n_grid, n_side):
+    """accumulate_kernel's 2x2x2 block expansion (gh_group_math.cuh) on a real grid, every sub-particle evaluated by
+    both the production fast paths and the exact fp64 path: no disagreement with the float-evaluation margins at 1,
+    1/2 and 1/4, and only a few per cent of the sub-particles left to the exact path."""
     from crime_b200 import GetHI, params_from_tables
-    assert os.environ.get("GH_ACC_TAYLOR"), "set GH_ACC_TAYLOR=1 together with GH_TEST_EXPERIMENTAL=1"
-    p = params_from_tables(tables_nu64, n_grid=256, n_side=256, seed=3)
+    p = params_from_tables(tables_nu64, n_grid=n_grid, n_side=n_side, seed=3)
     with GetHI(p) as g:
         g.create_d_and_vr_fields(); g.get_HI()
-        for scale in (1.0, 0.5):
+        for scale in (1.0, 0.5, 0.25):
             a = g.accumulate_audit(scale)
-            assert a["wrong"] == 0, a
+            assert a["wrong"] == 0, (scale, a)
+            assert a["out"] + a["inside"] + a["unsure"] == 10 * n_grid ** 3
             assert a["unsure"] < 0.03 * (a["inside"] + a["unsure"]), a
+
+
+@pytest.mark.parametrize("n_side,cells_full", [(1024, 2048), (2048, 4096)])
+@pytest.mark.parametrize("where", ["equator_seam", "pole", "cone"])
+def test_block_expansion_audit_fine_grid_geometry(tables_nu64, n_side, cells_full, where):
+    """The cell size of the 2048^3 / nside 1024 and 4096^3 / nside 2048 configurations on a 128^3 sub-box placed
+    (through pos_obs, which the C-ABI takes explicitly) on the +x axis across the tt = 0 seam, around the north pole,
+    and astride the |cos theta| = 2/3 cone: same audit, plus the maps of the production path against the exact path
+    run point by point."""
+    from crime_b200 import GetHI, params_from_tables
+    n = 128
+    p = params_from_tables(tables_nu64, n_grid=cells_full, n_side=n_side, seed=5)
+    dx = p.l_box / cells_full
+    lb = dx * n
+    p.n_grid, p.l_box = n, lb
+    r0 = 2200.0
+    if where == "equator_seam":
+        obs = (-r0, 0.5 * lb + 0.3 * dx, 0.5 * lb)
+    elif where == "pole":
+        obs = (0.5 * lb + 0.4 * dx, 0.5 * lb - 0.2 * dx, -r0)
+    else:  # |z| / r = 2/3 runs through the middle of the box
+        obs = (-r0 * 0.745356, 0.5 * lb, -r0 * 2.0 / 3.0 - 0.5 * lb)
+    for i in range(3):
+        p.pos_obs[i] = obs[i]
+    with GetHI(p) as g:
+        g.create_d_and_vr_fields(); g.get_HI()
+        tot = 10 * n ** 3
+        for scale in (1.0, 0.5, 0.25):
+            a = g.accumulate_audit(scale)
+            assert a["wrong"] == 0, (where, scale, a)
+            assert a["out"] + a["inside"] + a["unsure"] == tot
+        assert a["inside"] > 0.5 * tot, a                      # the sub-box sits inside the shells
+        a = g.accumulate_audit(1.0)
+        assert a["unsure"] < (0.05 if where != "pole" else 0.15) * tot, a
 
 
 def test_reference_own_driver_on_the_gpu_path(tmp_path):

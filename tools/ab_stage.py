@@ -2,8 +2,8 @@
 whole realisation, the map stage alone, the on-device audit of the fast path against the exact path, and the maps
 compared with the default build's.
 
-    python tools/ab_stage.py                      # default vs GH_ACC_TAYLOR=1 at 512^3
-    python tools/ab_stage.py 1024 512 150 GH_ACC_TAYLOR=1 GH_NO_FUSE_VEL=1
+    python tools/ab_stage.py                      # the default build alone at 512^3
+    python tools/ab_stage.py 1024 512 150 GH_NO_FUSE_VEL=1 GH_CUDA_LIB=crime_b200/csrc/variants/libgh_cuda_x.so
 """
 import json
 import os
@@ -39,7 +39,7 @@ def child(n, ns, nu):
 
 def main():
     args = [a for a in sys.argv[1:] if "=" not in a]
-    variants = [a for a in sys.argv[1:] if "=" in a] or ["GH_ACC_TAYLOR=1"]
+    variants = [a for a in sys.argv[1:] if "=" in a]
     n, ns, nu = (int(a) for a in (args + ["512", "256", "64"][len(args):])[:3])
     import numpy as np
     import tempfile
