@@ -186,8 +186,8 @@ GH_HD bool gh_sub_eq(float U, float V, float hm, int ns4, int pix0, int c_sum, i
   const bool ok = (fabsf(a - ra) < hm) && (fabsf(b - rb) < hm);
   const int jd = ba - bb;                                  // jp - jm
   int ip = (int)((unsigned)ba + (unsigned)bb + (unsigned)c_sum) >> 1;  // (jp + jm - ns + 1) >> 1, see test_taylor_pixelisation_cpu.py
-  const int ipw = ip - ns4;
-  ip = (ipw >= 0) ? ipw : ip;
+  const unsigned ipw = (unsigned)(ip - ns4);  // wraps to a huge value unless ip >= 4 ns
+  ip = (int)((unsigned)ip < ipw ? (unsigned)ip : ipw);
   pix = pix0 + jd * ns4 + ip;
   return ok;
 }

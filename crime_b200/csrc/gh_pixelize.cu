@@ -364,8 +364,8 @@ __device__ __noinline__ unsigned generic_cell(const GhDev &d, float eps_scale, d
 }
 
 // ---- accumulate_kernel ------------------------------------------------------------------------------------
-// One thread per 2 x 2 x 2 block of cells; a CTA of 16 x 8 threads covers 32 x 16 cells of a pair of planes, a warp
-// 32 x 4 x 2 cells, so that its lanes see nearly the same shells and the same HEALPix regime.
+// One thread per 2 x 2 x 2 block of cells; a warp covers 8 x 8 x 4 cells, so that its lanes see nearly the same
+// shells and the same HEALPix regime, a CTA of four warps 16 x 16 x 4 cells.
 //   1. Block cull: every sub-particle lies within sqrt(3) dx of the block centre and z_of_r is monotone, so their
 //      redshifts lie in [z(r_C - hg) + min dz, z(r_C + hg) + max dz]; blocks whose bracket misses the shells'
 //      redshift window are skipped (about 44 % of the box for the shipped frequency table).
@@ -394,6 +394,16 @@ __device__ __noinline__ unsigned generic_cell(const GhDev &d, float eps_scale, d
 #endif
 constexpr int kAccSubUnroll = GH_ACC_SUB_UNROLL;  // #pragma unroll takes a constant expression, not a macro
 
+// thread -> block of cells: a warp covers 4 x 4 x 2 blocks = 8 x 8 x 4 cells (compact, so that few warps straddle the
+// shells' radial window, the |cos theta| = 2/3 cones or the quadrant boundaries), the four warps of a CTA 16 x 16 x 4
+__device__ __forceinline__ void acc_block_of(int tid, int &cx, int &cy, int &pz0)
+{
+  const int lane = tid & 31, wid = tid >> 5;
+  cx = 2 * (blockIdx.x * 8 + (wid & 1) * 4 + (lane & 3));
+  cy = 2 * (blockIdx.y * 8 + (wid >> 1) * 4 + ((lane >> 2) & 3));
+  pz0 = 2 * (blockIdx.z * 2 + (lane >> 4));
+}
+
 template <bool AUDIT>
 __global__ void __launch_bounds__(128, GH_ACC_MIN_BLOCKS) accumulate_kernel(const __grid_constant__ GhDev d, const float *__restrict__ mass,
                                                          const float *__restrict__ dzrsd, float *__restrict__ maps,
@@ -405,13 +415,13 @@ __global__ void __launch_bounds__(128, GH_ACC_MIN_BLOCKS) accumulate_kernel(cons
   __shared__ float s_w[8][128], s_dz[8][128];
   __shared__ int s_nx, s_nc;
   const int ngx = 2 * d.nh;
-  const int tid = threadIdx.x + 16 * threadIdx.y;  // blockDim = (16, 8)
+  const int tid = threadIdx.x;
   if (tid == 0) { s_nx = 0; s_nc = 0; }
-  const int cx = 2 * (blockIdx.x * 16 + threadIdx.x), cy = 2 * (blockIdx.y * 8 + threadIdx.y);  // first cell of the block
-  const int pz0 = 2 * blockIdx.z;
+  int cx, cy, pz0;  // first cell of this thread's block, first plane relative to the launch
+  acc_block_of(tid, cx, cy, pz0);
   const int nzv = min(2, nplanes - pz0);
   const int zg = zg_base + pz0;
-  const bool active = (cx < d.n) && (cy < d.n);
+  const bool active = (cx < d.n) && (cy < d.n) && (nzv > 0);
   const unsigned valid = active ? (nzv == 2 ? 0xFFu : 0x0Fu) : 0u;
   AuditCounts ac = {0, 0, 0, 0};
   float dz_min = 3.0e38f, dz_max = -3.0e38f;
@@ -510,18 +520,20 @@ __global__ void __launch_bounds__(128, GH_ACC_MIN_BLOCKS) accumulate_kernel(cons
           edge_thresholds(fmaf(-ddz, gs.s1, gs.r1), eps, rc_hi, rc_lo, lo_b, hi_b);
           edge_thresholds(fmaf(-ddz, gs.s2, gs.r2), eps, rc_hi, rc_lo, lo_c, hi_c);
           unsigned need = 0u;
-#pragma unroll kAccSubUnroll
-          for (int isub = 0; isub < GH_CUDA_N_SUBPART; ++isub) {
+          // one sub-particle; `pol` is a literal at both call sites, so each loop carries only its own regime
+          auto sub = [&](int isub, bool pol) {
             const float4 o = d.sub_c[isub];
             const float S = gh_cell_S(ce, o.x, o.y, o.z, o.w);
             // shell: j0 inside the innermost edge, one less beyond each edge crossed; unsure within eps of an edge
             const bool p1 = S > hi_a, p2 = S > hi_b, p3 = S > hi_c;
             const bool sure = ((S < lo_a) || p1) && ((S < lo_b) || p2) && ((S < lo_c) || p3);
-            const int dj = (p1 ? 1 : 0) + (p2 ? 1 : 0) + (p3 ? 1 : 0);
+            int dj = p1 ? 1 : 0;
+            if (p2) dj++;
+            if (p3) dj++;
             const bool inside = (unsigned)(j0 - dj) < (unsigned)n_nu;
             const float U = gh_cell_U(g, ce, o.x, o.y), V = gh_cell_V(g, ce, o.x, o.y, o.z);
             int pix;
-            const bool ok = polar ? gh_sub_polar(U, V, hm, k_a, k_b, k_c, pix) : gh_sub_eq(U, V, hm, k_a, k_b, k_c, pix);
+            const bool ok = pol ? gh_sub_polar(U, V, hm, k_a, k_b, k_c, pix) : gh_sub_eq(U, V, hm, k_a, k_b, k_c, pix);
             if (!AUDIT) {
               if (sure && inside && ok) {
                 const int rel = dj * npix_neg + pix;
@@ -540,6 +552,13 @@ __global__ void __launch_bounds__(128, GH_ACC_MIN_BLOCKS) accumulate_kernel(cons
               else if (sure && ok) { ac.in++; if (j0 - dj != se || (long long)pix != pe) ac.wrong++; }
               else ac.unsure++;
             }
+          };
+          if (polar) {
+#pragma unroll kAccSubUnroll
+            for (int isub = 0; isub < GH_CUDA_N_SUBPART; ++isub) sub(isub, true);
+          } else {
+#pragma unroll kAccSubUnroll
+            for (int isub = 0; isub < GH_CUDA_N_SUBPART; ++isub) sub(isub, false);
           }
           if (!AUDIT && need) {
             int at = atomicAdd(&s_nx, __popc(need));
@@ -559,9 +578,11 @@ __global__ void __launch_bounds__(128, GH_ACC_MIN_BLOCKS) accumulate_kernel(cons
   for (int j = tid; j < ncells; j += 128) {
     const unsigned e = cqueue[j];
     const int src = e >> 3, c = e & 7;
-    const int sx = 2 * (blockIdx.x * 16 + (src & 15)) + (c & 1), sy = 2 * (blockIdx.y * 8 + (src >> 4)) + ((c >> 1) & 1);
+    int bx, by, bz;
+    acc_block_of(src, bx, by, bz);
+    const int sx = bx + (c & 1), sy = by + ((c >> 1) & 1), sz = zg_base + bz + (c >> 2);
     const double x0 = d.dx * (sx + 0.5) - d.pos_obs[0], y0 = d.dx * (sy + 0.5) - d.pos_obs[1];
-    const double z0 = d.dx * (zg + (c >> 2) + 0.5) - d.pos_obs[2];
+    const double z0 = d.dx * (sz + 0.5) - d.pos_obs[2];
     unsigned need = generic_cell<AUDIT>(d, eps_scale, x0, y0, z0, s_w[c][src], s_dz[c][src], maps, AUDIT ? &ac : nullptr);
     if (!AUDIT && need) {
       int at = atomicAdd(&s_nx, __popc(need));
@@ -587,10 +608,12 @@ __global__ void __launch_bounds__(128, GH_ACC_MIN_BLOCKS) accumulate_kernel(cons
   for (int j = tid; j < total; j += 128) {
     const unsigned e = xqueue[j];
     const int src = e >> 7, c = (e >> 4) & 7, isub = e & 15;
-    const int sx = 2 * (blockIdx.x * 16 + (src & 15)) + (c & 1), sy = 2 * (blockIdx.y * 8 + (src >> 4)) + ((c >> 1) & 1);
+    int bx, by, bz;
+    acc_block_of(src, bx, by, bz);
+    const int sx = bx + (c & 1), sy = by + ((c >> 1) & 1), sz = zg_base + bz + (c >> 2);
     const double px = d.dx * (sx + 0.5) - d.pos_obs[0] + d.sub_off[isub];
     const double py = d.dx * (sy + 0.5) - d.pos_obs[1] + d.sub_off[GH_CUDA_N_SUBPART + isub];
-    const double pz = d.dx * (zg + (c >> 2) + 0.5) - d.pos_obs[2] + d.sub_off[2 * GH_CUDA_N_SUBPART + isub];
+    const double pz = d.dx * (sz + 0.5) - d.pos_obs[2] + d.sub_off[2 * GH_CUDA_N_SUBPART + isub];
     long long ipix;
     const int inu = gh_point_to_shell_pixel(t, px, py, pz, (double)s_dz[c][src], &ipix);
     if (ipix >= 0) atomicAdd(maps + (size_t)ipix + (size_t)d.npix * inu, s_w[c][src]);
@@ -745,7 +768,7 @@ int gh_launch_accumulate(gh_cuda_ctx *c, const float *mass, const float *dzrsd, 
 {
   const GhDev &d = c->d;
   if (nplanes <= 0) return 0;
-  dim3 grid((d.n + 31) / 32, (d.n + 15) / 16, (nplanes + 1) / 2), block(16, 8);
+  dim3 grid((d.n + 15) / 16, (d.n + 15) / 16, (nplanes + 3) / 4), block(128);
   accumulate_kernel<false><<<grid, block, 0, c->stream>>>(d, mass, dzrsd, c->maps, 1.0f, nullptr, iz_base, zg_base, nplanes);
   GH_LAUNCH_CHECK(c);
   return 0;
@@ -754,7 +777,7 @@ int gh_launch_accumulate(gh_cuda_ctx *c, const float *mass, const float *dzrsd, 
 int gh_launch_accumulate_audit(gh_cuda_ctx *c, float eps_scale, unsigned long long *d_counts)
 {
   const GhDev &d = c->d;
-  dim3 grid((d.n + 31) / 32, (d.n + 15) / 16, (d.nz_here + 1) / 2), block(16, 8);
+  dim3 grid((d.n + 15) / 16, (d.n + 15) / 16, (d.nz_here + 3) / 4), block(128);
   const float *m = reinterpret_cast<const float *>(c->gridA), *z = reinterpret_cast<const float *>(c->gridC);
   accumulate_kernel<true><<<grid, block, 0, c->stream>>>(d, m, z, c->maps, eps_scale, d_counts, 0, d.iz0, d.nz_here);
   GH_LAUNCH_CHECK(c);
