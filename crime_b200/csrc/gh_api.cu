@@ -536,6 +536,8 @@ extern "C" int gh_cuda_create(const gh_cuda_params *p, int rank, int nranks, con
   }
   // gh_cuda_run*: radial velocity and get_HI in one pass (the multi-GPU parity check compares it with the staged calls)
   c->fuse_vel = getenv("GH_NO_FUSE_VEL") == nullptr;
+  c->fft_tma = getenv("GH_FFT_NO_TMA") == nullptr;
+  for (int i = 0; i < 4; ++i) c->fft_map_ok[i] = false;
   CREATE_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   CREATE_OK(cudaStreamCreateWithFlags(&c->pull_stream, cudaStreamNonBlocking));
   CREATE_OK(cudaEventCreateWithFlags(&c->ev_bar, cudaEventDisableTiming));

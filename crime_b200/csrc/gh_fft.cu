@@ -22,6 +22,8 @@
 // 8-byte accesses; the strided kernel's [position][line] tile is conflict-free as it is (lines are the fast
 // index in both global and shared memory), so it uses plain addressing.
 #include "gh_internal.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
 
 namespace {
 
@@ -120,11 +122,17 @@ template <> struct Swz<1024, 8> { static constexpr int a = 0, b = 6, c = 31; };
 template <> struct Swz<2048, 8> { static constexpr int a = 0, b = 1, c = 7; };
 template <> struct Swz<2048, 4> { static constexpr int a = 0, b = 6, c = 31; };
 
-template <int LEN, int W, bool SWZ = true> __device__ __forceinline__ int phys(int pos, int w)
+// tile layouts: LAY_PLAIN [position][line]; LAY_SWZ the same, XOR-swizzled; LAY_PAIR [position parity][position / 2][line],
+// which is how the TMA-fed y pass receives its tile (even and odd rows arrive as two boxes, see fft_strided_tma_kernel)
+enum { LAY_PLAIN = 0, LAY_SWZ = 1, LAY_PAIR = 2 };
+
+template <int LEN, int W, int LAY = LAY_SWZ> __device__ __forceinline__ int phys(int pos, int w)
 {
   using S = Swz<LEN, W>;
+  // odd rows: pitch W + 2, data from column 1 (their box starts one mode early to be 16-byte aligned)
+  if constexpr (LAY == LAY_PAIR) return (pos & 1) ? (LEN / 2) * W + (pos >> 1) * (W + 2) + 1 + w : (pos >> 1) * W + w;
   const int a = pos * W + w;
-  if constexpr (!SWZ) return a;
+  if constexpr (LAY == LAY_PLAIN) return a;
   const int l = a >> 4;
   int m = l >> S::a;
   if constexpr (S::b < 31) m ^= l >> S::b;
@@ -134,7 +142,7 @@ template <int LEN, int W, bool SWZ = true> __device__ __forceinline__ int phys(i
 
 // One in-place radix pass of a LEN-point decimation-in-frequency transform over a [LEN][W] tile.
 // NTW is the length of the twiddle table (exp(+2 pi i j/NTW)); LEN divides NTW.
-template <int LEN, int NTW, int W, int NT, int S, bool SWZ>
+template <int LEN, int NTW, int W, int NT, int S, int LAY>
 __device__ __forceinline__ void dif_pass_smem(float2 *sm, const float2 *__restrict__ tw)
 {
   constexpr int R = rad_at(LEN, S);
@@ -149,7 +157,7 @@ __device__ __forceinline__ void dif_pass_smem(float2 *sm, const float2 *__restri
     float2 u[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      addr[r] = phys<LEN, W, SWZ>(p0 + r * SUB, w);
+      addr[r] = phys<LEN, W, LAY>(p0 + r * SUB, w);
       u[r] = sm[addr[r]];
     }
     dft<R>(u);
@@ -174,13 +182,13 @@ struct StridedGeom {
   long long peer_chunk;
 };
 
-template <int N, int W, int NT, int S>
+template <int N, int W, int NT, int S, int LAY = LAY_PLAIN>
 __device__ __forceinline__ void strided_middle(float2 *sm, const float2 *__restrict__ tw)
 {
   if constexpr (S < n_steps(N) - 1) {
-    dif_pass_smem<N, N, W, NT, S, false>(sm, tw);
+    dif_pass_smem<N, N, W, NT, S, LAY>(sm, tw);
     __syncthreads();
-    strided_middle<N, W, NT, S + 1>(sm, tw);
+    strided_middle<N, W, NT, S + 1, LAY>(sm, tw);
   }
 }
 
@@ -215,7 +223,7 @@ __global__ void __launch_bounds__(NT) fft_strided_kernel(const float2 *__restric
       dft<R>(u);
       twiddle_powers<R>(u, __ldg(tw + i));
 #pragma unroll
-      for (int q = 0; q < R; ++q) sm[phys<N, W, false>(i + q * SUB, w)] = u[q];
+      for (int q = 0; q < R; ++q) sm[phys<N, W, LAY_PLAIN>(i + q * SUB, w)] = u[q];
     }
   }
   __syncthreads();
@@ -228,7 +236,131 @@ __global__ void __launch_bounds__(NT) fft_strided_kernel(const float2 *__restric
       const int w = item % W, b = item / W;
       float2 u[R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) u[r] = sm[phys<N, W, false>(b * R + r, w)];
+      for (int r = 0; r < R; ++r) u[r] = sm[phys<N, W, LAY_PLAIN>(b * R + r, w)];
+      dft<R>(u);
+      if (w < nvalid) {
+        const int f0 = dif_pos_to_freq<N>(b * R);
+        if (!g.peer_mode) {
+          float2 *o = dp + (long long)f0 * g.dst_stride + w;
+#pragma unroll
+          for (int q = 0; q < R; ++q) o[(long long)(q * (N / R)) * g.dst_stride] = u[q];
+        } else {
+#pragma unroll
+          for (int q = 0; q < R; ++q) {
+            const int f = f0 + q * (N / R);
+            const int owner = f / g.nz_peer, zl = f - owner * g.nz_peer;
+            peers.C[owner][(long long)g.me * g.peer_chunk + (long long)zl * g.dst_stride + l0 + w] = u[q];
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---- strided axis, tile fetched by the TMA unit ----------------------------------------------------
+// Same transform as fft_strided_kernel, but the [N][W] tile arrives in shared memory through cp.async.bulk.tensor
+// boxes issued by one thread and signalled on an mbarrier: no load instructions, no registers and no address
+// arithmetic are spent on the 8-byte-per-thread strided reads, and rows of W * 8 = 32..128 bytes stream at the
+// rate of a bulk copy (tools/tma_tile_probe.cu: 3.9-4.6 TB/s where the per-thread loads reach 2.1 at N >= 1024).
+// All radix passes then run out of shared memory and the last one scatters to global memory as before (to the
+// peers' receive buffers in the fused transpose).
+//   PAIR = false (z pass): the slab is a 2-D tensor {line (flat ky_local * nh + kx), kz}; its row pitch lines * 8 B
+//     is a multiple of 16 B because nky_here is even.
+//   PAIR = true (y pass): rows of one z plane are nh = N/2 + 1 modes long, an odd number, so the 8 nh-byte row pitch
+//     violates the TMA's 16-byte stride rule.  Two consecutive rows, however, form one 16 nh-byte "row pair": the
+//     tensor is {4 nh floats, rows / 2 pairs, plane, chunk} and a tile takes two boxes per block of pairs: the even
+//     rows at inner offset 2 kx0, W modes wide, and the odd rows through a second map whose box is W + 2 modes wide
+//     and starts at 2 (nh + kx0 - 1) -- box starts must be 16-byte aligned too (an odd start faults with "illegal
+//     instruction"), and nh + kx0 is odd --, so the odd rows sit one column to the right in their half of the
+//     LAY_PAIR tile.  chunk = the peer blocks of the received transpose ([q][z_local][ky_local][kx]).
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned phase)
+{
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(phase)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
+{
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3)
+{
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+                   smem_u32(dst)),
+               "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct TmaGeom {
+  int box_rows;   // rows (PAIR: row pairs) per box, <= 256
+  int nchunks;    // PAIR: peer blocks along the transformed axis (1 on one rank)
+  int nh;
+};
+
+template <int N, int W, int NT, bool PAIR>
+__global__ void __launch_bounds__(NT) fft_strided_tma_kernel(const __grid_constant__ CUtensorMap map, const __grid_constant__ CUtensorMap map_odd,
+                                                             float2 *__restrict__ dst,
+                                                             const float2 *__restrict__ tw, StridedGeom g, TmaGeom tg, GhPeers peers)
+{
+  extern __shared__ __align__(128) float2 sm[];
+  __shared__ uint64_t bar;
+  constexpr int LAY = PAIR ? LAY_PAIR : LAY_PLAIN;
+  const int tile = blockIdx.x;
+  const int grp_rel = tile / g.tiles_per_group;
+  const int grp = g.grp0 + grp_rel;
+  const int l0 = (tile - grp_rel * g.tiles_per_group) * W;
+  float2 *dp = dst + ((long long)grp * g.dst_group_stride + l0);
+  const int nvalid = min(W, g.lines_per_group - l0);
+  const int tid = threadIdx.x;
+  constexpr int NS = n_steps(N);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&bar, (unsigned)((N * W + (PAIR ? N : 0)) * sizeof(float2)));
+    if constexpr (!PAIR) {
+      for (int r = 0; r < N; r += tg.box_rows) tma_load_2d(sm + (size_t)r * W, &map, &bar, 2 * l0, r);
+    } else {
+      const int half = N / 2, ppc = half / tg.nchunks;  // row pairs per chunk
+      for (int q = 0; q < tg.nchunks; ++q) {
+        for (int j = 0; j < ppc; j += tg.box_rows) {
+          tma_load_4d(sm + (size_t)(q * ppc + j) * W, &map, &bar, 2 * l0, j, grp, q);
+          tma_load_4d(sm + (size_t)half * W + (size_t)(q * ppc + j) * (W + 2), &map_odd, &bar, 2 * (tg.nh + l0 - 1), j, grp, q);
+        }
+      }
+    }
+  }
+  __syncthreads();  // the barrier's initialisation is visible to everybody
+  while (!mbar_try_wait(&bar, 0)) {}
+  strided_middle<N, W, NT, 0, LAY>(sm, tw);
+  {
+    // last pass: shared -> registers -> global, scattered to natural order (block length R, SUB = 1)
+    constexpr int R = rad_at(N, NS - 1);
+#pragma unroll 1
+    for (int item = tid; item < W * (N / R); item += NT) {
+      const int w = item % W, b = item / W;
+      float2 u[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) u[r] = sm[phys<N, W, LAY>(b * R + r, w)];
       dft<R>(u);
       if (w < nvalid) {
         const int f0 = dif_pos_to_freq<N>(b * R);
@@ -254,7 +386,7 @@ template <int H, int NTW, int W, int NT, int S>
 __device__ __forceinline__ void rows_passes(float2 *sm, const float2 *__restrict__ tw)
 {
   if constexpr (S < n_steps(H)) {
-    dif_pass_smem<H, NTW, W, NT, S, true>(sm, tw);
+    dif_pass_smem<H, NTW, W, NT, S, LAY_SWZ>(sm, tw);
     __syncthreads();
     rows_passes<H, NTW, W, NT, S + 1>(sm, tw);
   }
@@ -337,6 +469,8 @@ template <int N, int WSEL = 0, int NTSEL = 0> struct FftCfg {
   static constexpr int W = WSEL ? WSEL : ((N <= 512) ? 16 : (N <= 2048 ? 8 : 4));  // strided tile width (lines)
   static constexpr int NT_S0 = (W * N / 16) < 64 ? 64 : ((W * N / 16) > 512 ? 512 : (W * N / 16));
   static constexpr int NT_S = NTSEL ? NTSEL : ((N <= 1024 && NT_S0 > 256) ? 256 : NT_S0);  // 3 CTAs/SM beat 2 fatter ones (profiles/)
+  static constexpr int WT = (N <= 512) ? 16 : (8192 / N);               // TMA-fed strided tile: 64 KB, 3 CTAs per SM
+  static constexpr int NT_T = (WT * N / 16) < 64 ? 64 : ((WT * N / 16) > 256 ? 256 : (WT * N / 16));
   static constexpr int WR = (N <= 1024) ? 16 : (N <= 2048 ? 8 : 4);     // rows per tile of the x pass
   static constexpr int NT_R = (WR * (N / 2) / 16) < 64 ? 64 : ((WR * (N / 2) / 16) > 512 ? 512 : (WR * (N / 2) / 16));
 };
@@ -350,6 +484,61 @@ int launch_strided(gh_cuda_ctx *c, const float2 *src, float2 *dst, const Strided
   GH_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long tiles = (long long)g.tiles_per_group * ngroups;
   kern<<<(unsigned)tiles, Cfg::NT_S, smem, c->stream>>>(src, dst, c->twiddle, g, c->peers);
+  GH_LAUNCH_CHECK(c);
+  return 0;
+}
+
+// ---- tensor maps of the TMA-fed strided passes ----------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 tma_encoder()
+{
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+  }
+  return fn;
+}
+
+// z pass: {2 * lines floats, n rows}, row pitch lines * 8 B
+static bool make_map_z(CUtensorMap *m, const float2 *base, long long lines, int n, int w, int box_rows)
+{
+  auto enc = tma_encoder();
+  if (!enc || (lines & 1) || 2 * lines > 0xffffffffLL) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)(2 * lines), (cuuint64_t)n};
+  const cuuint64_t strides[1] = {(cuuint64_t)lines * sizeof(float2)};
+  const cuuint32_t box[2] = {(cuuint32_t)(2 * w), (cuuint32_t)box_rows};
+  const cuuint32_t es[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// y pass: {4 nh floats (a pair of rows), rows_per_chunk / 2 pairs, planes, chunks}
+static bool make_map_y(CUtensorMap *m, const float2 *base, int nh, int rows_per_chunk, int planes, int nchunks, int w, int box_rows)
+{
+  auto enc = tma_encoder();
+  if (!enc || (rows_per_chunk % 16)) return false;  // whole boxes of >= 8 row pairs keep every box 128-byte aligned in shared memory
+  const cuuint64_t row = (cuuint64_t)nh * sizeof(float2);
+  const cuuint64_t dims[4] = {(cuuint64_t)(4 * nh), (cuuint64_t)(rows_per_chunk / 2), (cuuint64_t)planes, (cuuint64_t)nchunks};
+  const cuuint64_t strides[3] = {2 * row, row * rows_per_chunk, row * rows_per_chunk * planes};
+  const cuuint32_t box[4] = {(cuuint32_t)(2 * w), (cuuint32_t)box_rows, 1, 1};
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int N, bool PAIR>
+int launch_strided_tma(gh_cuda_ctx *c, const CUtensorMap &map, const CUtensorMap &map_odd, float2 *dst, StridedGeom g, const TmaGeom &tg,
+                       int ngroups)
+{
+  using Cfg = FftCfg<N>;
+  auto kern = fft_strided_tma_kernel<N, Cfg::WT, Cfg::NT_T, PAIR>;
+  const size_t smem = ((size_t)N * Cfg::WT + (PAIR ? N : 0)) * sizeof(float2);
+  GH_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  g.tiles_per_group = (g.lines_per_group + Cfg::WT - 1) / Cfg::WT;
+  const long long tiles = (long long)g.tiles_per_group * ngroups;
+  kern<<<(unsigned)tiles, Cfg::NT_T, smem, c->stream>>>(map, map_odd, dst, c->twiddle, g, tg, c->peers);
   GH_LAUNCH_CHECK(c);
   return 0;
 }
@@ -392,7 +581,16 @@ int fft_field(gh_cuda_ctx *c, float2 *field)
     // peers must be done with their receive buffers (previous field's y pass, previous realisation's maps)
     if (g.peer_mode && gh_stream_barrier(c)) return 1;
     if (c->time_fft_passes) cudaEventRecord(c->ev_pass[field == c->gridA ? 0 : 1][0], c->stream);
-    if (launch_strided<N, WSEL, NTSEL>(c, field, field, g, 1)) return 1;
+    const int mi = (field == c->gridA) ? 0 : 1;
+    TmaGeom tg;
+    tg.box_rows = N < 256 ? N : 256; tg.nchunks = 1; tg.nh = nh;
+    if (c->fft_tma && (field == c->gridA || field == c->gridB) && !c->fft_map_ok[mi])
+      c->fft_map_ok[mi] = make_map_z(&c->fft_map[mi], field, g.lines_per_group, N, Cfg::WT, tg.box_rows);
+    if (c->fft_tma && (field == c->gridA || field == c->gridB) && c->fft_map_ok[mi]) {
+      if (launch_strided_tma<N, false>(c, c->fft_map[mi], c->fft_map[mi], field, g, tg, 1)) return 1;
+    } else {
+      if (launch_strided<N, WSEL, NTSEL>(c, field, field, g, 1)) return 1;
+    }
   }
   const float2 *ysrc = field;
   StridedGeom g;
@@ -438,7 +636,18 @@ int fft_field(gh_cuda_ctx *c, float2 *field)
   for (int z0 = 0; z0 < d.nz_here; z0 += nb) {
     const int nz = (d.nz_here - z0 < nb) ? d.nz_here - z0 : nb;
     g.grp0 = z0;
-    if (launch_strided<N, WSEL, NTSEL>(c, ysrc, field, g, nz)) return 1;
+    // TMA-fed y pass: the source is this field's slab on one rank, the transpose receive buffer on several
+    const int mi = (field == c->gridA) ? 2 : 3;
+    const int nchunks = d.nranks > 1 ? d.nranks : 1, rows_per_chunk = N / nchunks;
+    TmaGeom tg;
+    tg.box_rows = rows_per_chunk / 2 < 256 ? rows_per_chunk / 2 : 256; tg.nchunks = nchunks; tg.nh = nh;
+    const bool tma_src = (field == c->gridA || field == c->gridB);
+    if (c->fft_tma && tma_src && !c->fft_map_ok[mi])
+      c->fft_map_ok[mi] = make_map_y(&c->fft_map[mi], ysrc, nh, rows_per_chunk, d.nz_here, nchunks, Cfg::WT, tg.box_rows) &&
+                          make_map_y(&c->fft_map[mi + 2], ysrc, nh, rows_per_chunk, d.nz_here, nchunks, Cfg::WT + 2, tg.box_rows);
+    if (c->fft_tma && tma_src && c->fft_map_ok[mi]) {
+      if (launch_strided_tma<N, true>(c, c->fft_map[mi], c->fft_map[mi + 2], field, g, tg, nz)) return 1;
+    } else if (launch_strided<N, WSEL, NTSEL>(c, ysrc, field, g, nz)) return 1;
     const long long first_block = ((long long)z0 * d.n) / Cfg::WR;
     if (field == c->gridA) {
       if (launch_rows<N, true>(c, field + (size_t)z0 * d.n * nh, (long long)nz * d.n, (float)normd, first_block)) return 1;

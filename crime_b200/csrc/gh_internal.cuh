@@ -1,6 +1,7 @@
 // Internal declarations shared by the translation units of libgh_cuda.so.
 // B200 (sm_100a) only; no CPU fallback exists anywhere in this library.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <nccl.h>
 #include <stdint.h>
@@ -115,6 +116,9 @@ struct gh_cuda_ctx {
   int n_sm;
   int fft_stats_blocks;    // >0: the density FFT left that many per-CTA (sum, sumsq) partials in d_partials
   size_t fft_batch_bytes;  // plane batch of the fused y/x FFT passes (kept L2-resident)
+  bool fft_tma;            // strided FFT passes fetch their tiles with the TMA unit (GH_FFT_NO_TMA=1 turns it off)
+  CUtensorMap fft_map[6];  // z pass of A, of B; y pass of A, of B: even rows; odd rows (wider box, see gh_fft.cu)
+  bool fft_map_ok[4];
 };
 
 void gh_set_error(const char *fmt, ...);
