@@ -536,7 +536,10 @@ extern "C" int gh_cuda_create(const gh_cuda_params *p, int rank, int nranks, con
   }
   // gh_cuda_run*: radial velocity and get_HI in one pass (the multi-GPU parity check compares it with the staged calls)
   c->fuse_vel = getenv("GH_NO_FUSE_VEL") == nullptr;
-  c->fft_tma = getenv("GH_FFT_NO_TMA") == nullptr;
+  // TMA-fed strided FFT passes: measured faster up to 512 (1.66 -> 1.56 ms both fields at 512^3), equal at 1024 (16.2 vs 16.4 ms),
+  // slower at 2048 where the 64 KB tile is only 4 lines wide and the 32-byte store rows dominate (217 vs 168 ms on one GPU;
+  // profiles/r2/): on by default for n_grid <= 512, GH_FFT_TMA=1 / GH_FFT_NO_TMA=1 force it on / off
+  c->fft_tma = getenv("GH_FFT_NO_TMA") == nullptr && (p->n_grid <= 512 || getenv("GH_FFT_TMA") != nullptr);
   for (int i = 0; i < 4; ++i) c->fft_map_ok[i] = false;
   CREATE_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   CREATE_OK(cudaStreamCreateWithFlags(&c->pull_stream, cudaStreamNonBlocking));
