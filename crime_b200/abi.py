@@ -151,6 +151,9 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         "gh_cuda_fastpath_audit": ([vp, vp, vp, C.c_longlong, C.c_double, vp], i32),
         "gh_cuda_accumulate_audit": ([vp, C.c_double, vp], i32),
         "gh_cuda_stage_times": ([vp, f64p], i32),
+        "gh_cuda_jt_merge_maps": ([vp, i32, C.POINTER(vp), f64p, C.c_long, vp], i32),
+        "gh_cuda_udgrade": ([vp, vp, C.c_long, vp, C.c_long, i32, i32], i32),
+        "gh_cuda_nest_ring": ([vp, C.c_long, vp, vp, C.c_longlong, i32], i32),
         "gh_cuda_kernel_launches": ([vp], u64),
         "gh_cuda_stream": ([vp], vp),
         "gh_cuda_last_error": ([], C.c_char_p),
@@ -173,5 +176,6 @@ EXPORTED_SYMBOLS = (
     "gh_cuda_set_delta_k", "gh_cuda_clear_delta_k", "gh_cuda_download_delta_k", "gh_cuda_download_grid",
     "gh_cuda_upload_grid", "gh_cuda_set_sigma2_gauss", "gh_cuda_grid_checksum", "gh_cuda_download_maps", "gh_cuda_zero_maps",
     "gh_cuda_subparticle_offsets", "gh_cuda_points_to_shell_pixel", "gh_cuda_fastpath_audit", "gh_cuda_accumulate_audit", "gh_cuda_stage_times",
+    "gh_cuda_jt_merge_maps", "gh_cuda_udgrade", "gh_cuda_nest_ring",
     "gh_cuda_kernel_launches", "gh_cuda_stream", "gh_cuda_last_error", "gh_cuda_version",
 )

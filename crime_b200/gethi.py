@@ -254,6 +254,39 @@ class GetHI:
         self._check(self.lib.gh_cuda_accumulate_audit(self._ctx, float(eps_scale), _ptr(cnt)))
         return dict(out=int(cnt[0]), inside=int(cnt[1]), unsure=int(cnt[2]), wrong=int(cnt[3]))
 
+    # -- JoinT ingestion -----------------------------------------------------------
+    def jt_merge_maps(self, components, nside_out: int, scale=None) -> np.ndarray:
+        """merge_maps (src/main_jt.c:98-211) for this rank's shells: `components` is the list of component stacks in
+        the reference's order, each a float32 array [n_shells_here][npix] or None for the stack mk_T_maps / run just
+        left on the device (the cosmological signal); the sum is degraded / upgraded to nside_out by he_udgrade
+        (src/healpix_extra.c:318-385).  Returns [n_shells_here][12 nside_out^2]."""
+        n = len(components)
+        keep = [None if c is None else np.ascontiguousarray(c, dtype=np.float32) for c in components]
+        for c in keep:
+            if c is not None and c.shape != (self.n_shells_here, self.npix):
+                raise ValueError(f"component stack must be [{self.n_shells_here}][{self.npix}], got {c.shape}")
+        ptrs = (C.c_void_p * n)(*[None if c is None else c.ctypes.data for c in keep])
+        sc = None if scale is None else (C.c_double * n)(*[float(v) for v in scale])
+        out = np.empty((self.n_shells_here, 12 * nside_out * nside_out), np.float32)
+        self._check(self.lib.gh_cuda_jt_merge_maps(self._ctx, n, ptrs, sc, int(nside_out), _ptr(out)))
+        return out
+
+    def udgrade(self, maps, nside_out: int, nest: bool = False) -> np.ndarray:
+        """he_udgrade (src/healpix_extra.c:318-385) of one map or a stack of maps held in host memory."""
+        m = np.ascontiguousarray(maps, dtype=np.float32)
+        stack = m.reshape(1, -1) if m.ndim == 1 else m
+        nside_in = int(round((stack.shape[1] / 12) ** 0.5))
+        out = np.empty((stack.shape[0], 12 * nside_out * nside_out), np.float32)
+        self._check(self.lib.gh_cuda_udgrade(self._ctx, _ptr(stack), nside_in, _ptr(out), int(nside_out), int(nest), stack.shape[0]))
+        return out[0] if m.ndim == 1 else out
+
+    def nest_ring(self, nside: int, pix, to_ring: bool) -> np.ndarray:
+        """chealpix nest2ring (to_ring) / ring2nest through the device code of the two calls above."""
+        a = np.ascontiguousarray(pix, dtype=np.int64)
+        out = np.empty_like(a)
+        self._check(self.lib.gh_cuda_nest_ring(self._ctx, int(nside), _ptr(a), _ptr(out), a.size, int(to_ring)))
+        return out
+
     def stage_times(self) -> dict:
         ms = (C.c_double * len(STAGE_NAMES))()
         self._check(self.lib.gh_cuda_stage_times(self._ctx, ms))

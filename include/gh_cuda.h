@@ -224,6 +224,23 @@ int gh_cuda_stage_times(gh_cuda_ctx *ctx, double *ms_out);
  * z_ms[0] = density, z_ms[1] = velocity potential; -1 when off. */
 int gh_cuda_fft_pass_times(gh_cuda_ctx *ctx, double *z_ms);
 
+/* ---- JoinT ingestion of GetHI output on the device ----
+ * gh_cuda_jt_merge_maps replaces merge_maps (src/main_jt.c:98-211) for the shells this rank owns: for every shell,
+ * map_in = 0, then the n_comp components are added in the order given (the reference's order: cosmological signal,
+ * extragalactic free-free, galactic free-free, point sources, [polarised synchrotron * polarization_leakage,]
+ * synchrotron, custom), then he_udgrade(map_in, n_side -> nside_out, RING) (src/healpix_extra.c:318-385) and the
+ * result goes to out_host[n_shells_here][12 nside_out^2].  comp_host[k] is a HOST stack [n_shells_here][12 n_side^2]
+ * of this rank's shells, or NULL for the stack gh_cuda_mk_T_maps / gh_cuda_run has just left on the device -- the
+ * cosmological signal enters the sum without a FITS round trip.  scale[k] (may be NULL = all 1) multiplies
+ * component k as `map_read[ii] *= leakage` does (float * double -> float, src/main_jt.c:183).
+ * Bit-identical to the reference: float adds in the same order, double sum over the NEST children in child order.
+ * gh_cuda_udgrade is he_udgrade alone on n_maps host maps (nest = 0: RING ordering). */
+int gh_cuda_jt_merge_maps(gh_cuda_ctx *ctx, int n_comp, const float *const *comp_host, const double *scale, long nside_out,
+                          float *out_host);
+int gh_cuda_udgrade(gh_cuda_ctx *ctx, const float *maps_in, long nside_in, float *maps_out, long nside_out, int nest, int n_maps);
+/* chealpix nest2ring (to_ring != 0) / ring2nest through the device code the two calls above use */
+int gh_cuda_nest_ring(gh_cuda_ctx *ctx, long nside, const long long *pix_in, long long *pix_out, long long n, int to_ring);
+
 /* launches of our own kernels issued by this context since creation */
 unsigned long long gh_cuda_kernel_launches(const gh_cuda_ctx *ctx);
 /* the CUDA stream (cudaStream_t as void*) all work of this context is enqueued on */

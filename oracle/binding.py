@@ -203,6 +203,25 @@ class Oracle:
         self.lib.oracle_pix2vec_ring(nside, ipix, _ptr(v))
         return v
 
+    def nest2ring(self, nside: int, pix) -> np.ndarray:
+        self.lib.oracle_nest2ring.restype = C.c_long
+        self.lib.oracle_nest2ring.argtypes = [C.c_long, C.c_long]
+        return np.array([self.lib.oracle_nest2ring(nside, int(i)) for i in np.atleast_1d(pix)], np.int64)
+
+    def ring2nest(self, nside: int, pix) -> np.ndarray:
+        self.lib.oracle_ring2nest.restype = C.c_long
+        self.lib.oracle_ring2nest.argtypes = [C.c_long, C.c_long]
+        return np.array([self.lib.oracle_ring2nest(nside, int(i)) for i in np.atleast_1d(pix)], np.int64)
+
+    def udgrade(self, map_in: np.ndarray, nside_out: int, nest: bool = False) -> np.ndarray:
+        """he_udgrade (src/healpix_extra.c:318-385) restated."""
+        m = np.ascontiguousarray(map_in, dtype=np.float32)
+        nside_in = int(round((m.size / 12) ** 0.5))
+        out = np.zeros(12 * nside_out * nside_out, np.float32)
+        self.lib.oracle_udgrade.argtypes = [_vp, C.c_long, _vp, C.c_long, C.c_int]
+        self.lib.oracle_udgrade(_ptr(m), nside_in, _ptr(out), nside_out, int(nest))
+        return out
+
     def run(self, p: GhCudaParams, dens_k=None, vpot_k=None):
         """Whole hot path on one slab; Philox stream unless a k-space field is supplied."""
         if dens_k is None:

@@ -91,3 +91,104 @@ void oracle_pix2vec_ring(long nside, long ipix, double vec[3])
   vec[1] = st * sin(phi);
   vec[2] = z;
 }
+
+/* ---- RING <-> NEST ------------------------------------------------------------------------------------- */
+static const int kJrll[12] = {2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4};
+static const int kJpll[12] = {1, 3, 5, 7, 0, 2, 4, 6, 1, 3, 5, 7};
+
+static long compress_bits(long v) /* every second bit of v, packed */
+{
+  long r = 0;
+  for (int b = 0; b < 31; ++b) r |= ((v >> (2 * b)) & 1L) << b;
+  return r;
+}
+static long spread_bits(long v) /* bit b of v -> bit 2b */
+{
+  long r = 0;
+  for (int b = 0; b < 31; ++b) r |= ((v >> b) & 1L) << (2 * b);
+  return r;
+}
+
+static long isqrt_long(long v)
+{
+  long r = (long)sqrt((double)v + 0.5);
+  while (r * r > v) --r;
+  while ((r + 1) * (r + 1) <= v) ++r;
+  return r;
+}
+
+long oracle_nest2ring(long nside, long ipnest)
+{
+  const long npface = nside * nside, npix = 12 * npface, nl4 = 4 * nside, ncap = 2 * nside * (nside - 1);
+  const long face = ipnest / npface, ipf = ipnest % npface;
+  const long ix = compress_bits(ipf), iy = compress_bits(ipf >> 1);
+  const long jr = kJrll[face] * nside - ix - iy - 1;
+  long nr = nside, n_before = ncap + nl4 * (jr - nside), kshift = (jr - nside) & 1;
+  if (jr < nside) { nr = jr; n_before = 2 * nr * (nr - 1); kshift = 0; }
+  else if (jr > 3 * nside) { nr = nl4 - jr; n_before = npix - 2 * (nr + 1) * nr; kshift = 0; }
+  long jp = (kJpll[face] * nr + ix - iy + 1 + kshift) / 2;
+  if (jp > nl4) jp -= nl4;
+  if (jp < 1) jp += nl4;
+  return n_before + jp - 1;
+}
+
+long oracle_ring2nest(long nside, long ipring)
+{
+  const long npix = 12 * nside * nside, nl2 = 2 * nside, nl4 = 4 * nside, ncap = 2 * nside * (nside - 1);
+  long irn, iphi, nr, kshift, face;
+  if (ipring < ncap) { /* north polar cap */
+    irn = (1 + isqrt_long(1 + 2 * ipring)) / 2; /* ring counted from the north pole */
+    iphi = ipring + 1 - 2 * irn * (irn - 1);
+    kshift = 0;
+    nr = irn;
+    face = (iphi - 1) / nr;
+  } else if (ipring < npix - ncap) { /* equatorial belt */
+    const long ip = ipring - ncap;
+    irn = ip / nl4 + nside;
+    iphi = ip % nl4 + 1;
+    kshift = (irn + nside) & 1;
+    nr = nside;
+    const long ire = irn - nside + 1, irm = nl2 + 2 - ire;
+    const long ifm = (iphi - ire / 2 + nside - 1) / nside, ifp = (iphi - irm / 2 + nside - 1) / nside;
+    if (ifp == ifm) face = (ifp == 4) ? 4 : ifp + 4;
+    else if (ifp < ifm) face = ifp;
+    else face = ifm + 8;
+  } else { /* south polar cap */
+    const long ip = npix - ipring;
+    const long irs = (1 + isqrt_long(2 * ip - 1)) / 2; /* ring counted from the south pole */
+    iphi = 4 * irs + 1 - (ip - 2 * irs * (irs - 1));
+    kshift = 0;
+    nr = irs;
+    irn = nl4 - irs;
+    face = (iphi - 1) / nr + 8;
+  }
+  const long irt = irn - kJrll[face] * nside + 1;
+  long ipt = 2 * iphi - kJpll[face] * nr - kshift - 1;
+  if (ipt >= nl2) ipt -= 8 * nside;
+  const long ix = (ipt - irt) / 2, iy = (-(ipt + irt)) / 2;
+  return face * nside * nside + spread_bits(ix) + 2 * spread_bits(iy);
+}
+
+void oracle_udgrade(const float *map_in, long nside_in, float *map_out, long nside_out, int nest)
+{
+  const long npix_in = 12 * nside_in * nside_in, npix_out = 12 * nside_out * nside_out;
+  if (nside_in == nside_out) {
+    for (long i = 0; i < npix_out; ++i) map_out[i] = map_in[i];
+  } else if (nside_in > nside_out) {
+    const long ratio = npix_in / npix_out;
+    const double inv = 1. / ((double)ratio);
+    for (long i = 0; i < npix_out; ++i) {
+      double tot = 0;
+      const long base = ratio * (nest ? i : oracle_ring2nest(nside_out, i));
+      for (long j = 0; j < ratio; ++j) tot += map_in[nest ? base + j : oracle_nest2ring(nside_in, base + j)];
+      map_out[i] = tot * inv;
+    }
+  } else {
+    const long ratio = npix_out / npix_in;
+    for (long i = 0; i < npix_in; ++i) {
+      const float v = map_in[i];
+      const long base = ratio * (nest ? i : oracle_ring2nest(nside_in, i));
+      for (long j = 0; j < ratio; ++j) map_out[nest ? base + j : oracle_nest2ring(nside_out, base + j)] = v;
+    }
+  }
+}

@@ -1,6 +1,6 @@
 /* TEST INFRASTRUCTURE ONLY -- stand-in for <chealpix.h> (HEALPix C library >= 3.10, unpinned).
  * nside2npix and vec2pix_ring restate the public HEALPix RING-scheme formulae (newer `sth`
- * variant, see oracle/healpix_ring.c); nest2ring / ring2nest are link-only for GetHI. */
+ * variant, see oracle/healpix_ring.c); nest2ring / ring2nest (used by JoinT's he_udgrade) forward to the same file. */
 #ifndef SHIM_CHEALPIX_H
 #define SHIM_CHEALPIX_H
 long nside2npix(long nside);

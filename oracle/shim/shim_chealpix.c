@@ -6,13 +6,5 @@
 
 long nside2npix(long nside) { return oracle_nside2npix(nside); }
 void vec2pix_ring(long nside, const double *vec, long *ipix) { *ipix = oracle_vec2pix_ring(nside, vec); }
-void nest2ring(long nside, long ipnest, long *ipring)
-{
-  (void)nside; (void)ipnest; (void)ipring;
-  fprintf(stderr, "shim_chealpix: nest2ring is link-only for GetHI\n"); abort();
-}
-void ring2nest(long nside, long ipring, long *ipnest)
-{
-  (void)nside; (void)ipring; (void)ipnest;
-  fprintf(stderr, "shim_chealpix: ring2nest is link-only for GetHI\n"); abort();
-}
+void nest2ring(long nside, long ipnest, long *ipring) { *ipring = oracle_nest2ring(nside, ipnest); }
+void ring2nest(long nside, long ipring, long *ipnest) { *ipnest = oracle_ring2nest(nside, ipring); }
