@@ -102,6 +102,27 @@ def params_to_dict(p: GhCudaParams) -> dict:
     return d
 
 
+class GhCudaPsourcesParams(C.Structure):
+    """gh_cuda_psources_params of include/gh_cuda.h (point sources)."""
+    _fields_ = [("nz", C.c_int), ("z_max", C.c_double), ("nz_arr", _dp), ("bias_arr", _dp), ("nl", C.c_int), ("logl_min", C.c_double),
+                ("logl_max", C.c_double), ("lcdf", _dp), ("nsed", C.c_int), ("lognu_min", C.c_double), ("lognu_max", C.c_double),
+                ("sed_arr", _dp), ("hhub", C.c_double)]
+
+
+def psources_params(nz_arr, bias_arr, lcdf, sed_arr, *, z_max, logl_min, logl_max, lognu_min, lognu_max, hhub) -> GhCudaPsourcesParams:
+    """Build the block from numpy tables (kept alive on the returned object)."""
+    import numpy as np
+    keep = {k: np.ascontiguousarray(v, dtype=np.float64) for k, v in dict(nz_arr=nz_arr, bias_arr=bias_arr, lcdf=lcdf, sed_arr=sed_arr).items()}
+    nz = keep["nz_arr"].size
+    p = GhCudaPsourcesParams()
+    p.nz, p.z_max, p.nl, p.logl_min, p.logl_max = nz, z_max, keep["lcdf"].size // nz - 1, logl_min, logl_max
+    p.nsed, p.lognu_min, p.lognu_max, p.hhub = keep["sed_arr"].size, lognu_min, lognu_max, hhub
+    for k, a in keep.items():
+        setattr(p, k, a.ctypes.data_as(_dp))
+    p._keep = keep
+    return p
+
+
 def load_library(path: os.PathLike | None = None) -> C.CDLL:
     """Load libgh_cuda.so and declare every entry point of include/gh_cuda.h.  Raises if absent."""
     path = Path(path) if path else Path(os.environ.get("GH_CUDA_LIB", LIB_PATH))  # GH_CUDA_LIB: A/B-testing a build
@@ -151,6 +172,9 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         "gh_cuda_fastpath_audit": ([vp, vp, vp, C.c_longlong, C.c_double, vp], i32),
         "gh_cuda_accumulate_audit": ([vp, C.c_double, vp], i32),
         "gh_cuda_stage_times": ([vp, f64p], i32),
+        "gh_cuda_get_point_sources": ([vp, C.POINTER(GhCudaPsourcesParams), C.POINTER(C.c_longlong)], i32),
+        "gh_cuda_mk_psources_maps": ([vp, vp], i32),
+        "gh_cuda_download_point_sources": ([vp, vp, vp], i32),
         "gh_cuda_jt_merge_maps": ([vp, i32, C.POINTER(vp), f64p, C.c_long, vp], i32),
         "gh_cuda_udgrade": ([vp, vp, C.c_long, vp, C.c_long, i32, i32], i32),
         "gh_cuda_nest_ring": ([vp, C.c_long, vp, vp, C.c_longlong, i32], i32),
@@ -176,6 +200,7 @@ EXPORTED_SYMBOLS = (
     "gh_cuda_set_delta_k", "gh_cuda_clear_delta_k", "gh_cuda_download_delta_k", "gh_cuda_download_grid",
     "gh_cuda_upload_grid", "gh_cuda_set_sigma2_gauss", "gh_cuda_grid_checksum", "gh_cuda_download_maps", "gh_cuda_zero_maps",
     "gh_cuda_subparticle_offsets", "gh_cuda_points_to_shell_pixel", "gh_cuda_fastpath_audit", "gh_cuda_accumulate_audit", "gh_cuda_stage_times",
+    "gh_cuda_get_point_sources", "gh_cuda_mk_psources_maps", "gh_cuda_download_point_sources",
     "gh_cuda_jt_merge_maps", "gh_cuda_udgrade", "gh_cuda_nest_ring",
     "gh_cuda_kernel_launches", "gh_cuda_stream", "gh_cuda_last_error", "gh_cuda_version",
 )

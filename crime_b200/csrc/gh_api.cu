@@ -283,12 +283,13 @@ static int apply_params(gh_cuda_ctx *c, const gh_cuda_params *p, int rank, int n
     // src/pixelize.c:155,246-256
     const double m2t = 90.057156 * p->OmegaB * p->hhub * (double)d.npix / (4 * M_PI);
     for (int inu = 0; inu < d.n_nu_pad; ++inu) {
-      if (inu >= p->n_nu) { c->h_prefac[inu] = 0; continue; }
+      if (inu >= p->n_nu) { c->h_prefac[inu] = 0; c->h_nu_centre[inu] = 1; continue; }
       double dnu, nu;
       if (p->irregular_nutable) { dnu = p->nuf_arr[inu] - p->nu0_arr[inu]; nu = (p->nuf_arr[inu] + p->nu0_arr[inu]) * 0.5; }
       else { dnu = (p->nu_max - p->nu_min) / p->n_nu; nu = p->nu_min + (inu + 0.5) * dnu; }
       const double r = host_r_of_z(p, GH_CUDA_NU_21 / nu - 1);
       c->h_prefac[inu] = m2t / (r * r * dnu);
+      c->h_nu_centre[inu] = nu;
     }
   }
   if (nranks > 1) {
@@ -378,7 +379,7 @@ static int setup_peers(gh_cuda_ctx *c)
   return 0;
 }
 
-// Opt-in (GH_SPARSE_REDUCE=1): map every peer's accumulation stack too, for the sparse map reduction
+// Map every peer's accumulation stack too, for the sparse map reduction (default; GH_NO_SPARSE_REDUCE=1 turns it off)
 // (gh_pixelize.cu).  Same handle exchange as setup_peers; a failure anywhere turns the feature off everywhere.
 static int setup_map_peers(gh_cuda_ctx *c)
 {
@@ -429,6 +430,7 @@ extern "C" int gh_cuda_destroy(gh_cuda_ctx *c)
   if (!c) return 0;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  gh_psources_release(c);
   if (c->have_comm && c->d_barrier) {
     // nobody may free a slab a peer could still be reading
     ncclAllReduce(c->d_barrier, c->d_barrier, 1, ncclInt, ncclSum, c->comm, c->stream);
@@ -612,7 +614,9 @@ extern "C" int gh_cuda_create(const gh_cuda_params *p, int rank, int nranks, con
     }
     c->have_comm = true;
     if (setup_peers(c)) { gh_cuda_destroy(c); return 1; }
-    if (c->have_peers && getenv("GH_SPARSE_REDUCE") && setup_map_peers(c)) { gh_cuda_destroy(c); return 1; }
+    // sparse map reduction over peer memory: validated against the single-GPU run on 2 and 4 GPUs and 1.9x faster than
+    // ncclReduceScatter there (profiles/r2/); GH_NO_SPARSE_REDUCE=1 restores the NCCL collective
+    if (c->have_peers && !getenv("GH_NO_SPARSE_REDUCE") && setup_map_peers(c)) { gh_cuda_destroy(c); return 1; }
   }
   CREATE_OK(cudaStreamSynchronize(c->stream));
 #undef CREATE_OK

@@ -107,6 +107,7 @@ struct gh_cuda_ctx {
   void *d_tables;                 // one allocation holding all small tables
   size_t tables_bytes;
   double h_prefac[4096];
+  double h_nu_centre[4096];       // shell centres (src/pixelize.c:63-70), for the point-source maps
   bool k_injected;
   bool sigma_overridden;
   double sigma2_gauss, mean_gauss;
@@ -170,5 +171,6 @@ int gh_launch_shell_extents(gh_cuda_ctx *c, int *ext_lo, int *ext_hi);
 int gh_launch_sparse_reduce(gh_cuda_ctx *c, const int *all_ext, float *out, int shell0, int nshells);
 int gh_launch_fastpath_audit(gh_cuda_ctx *c, const double *d_pos, const double *d_dz, long long n, float eps_scale,
                               unsigned long long *d_counts);
+void gh_psources_release(gh_cuda_ctx *c);  // frees the point-source state of a context (gh_psources.cu)
 int gh_launch_points(gh_cuda_ctx *c, const double *d_pos, const double *d_dz, long long n, int *d_shell,
                      long long *d_pix);

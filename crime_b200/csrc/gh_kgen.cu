@@ -15,23 +15,9 @@
 // Layout written: [kz][ky_local][kx], ky_local in this rank's ky slab -- ready for a local z transform.
 // Write-only, 16 B/mode (two complex-float fields), coalesced 16-byte stores (a pair of adjacent modes per thread).
 #include "gh_internal.cuh"
+#include "gh_philox.cuh"
 
 namespace {
-
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1, uint32_t &o0,
-                                              uint32_t &o1, uint32_t &o2, uint32_t &o3)
-{
-  uint32_t c2 = 0u, c3 = 0u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  o0 = c0; o1 = c1; o2 = c2; o3 = c3;
-}
 
 __device__ __forceinline__ int signed_idx(int i, int n) { return (2 * i <= n) ? i : i - n; }
 

@@ -675,7 +675,8 @@ __global__ void __launch_bounds__(256) scale_maps_kernel(float4 *__restrict__ ma
 }
 
 // ------------------------------------------------------------------------------------------------
-// Sparse map reduction over peer memory (opt-in, GH_SPARSE_REDUCE=1; several ranks with peer mappings).
+// Sparse map reduction over peer memory (several ranks with peer mappings; GH_NO_SPARSE_REDUCE=1 falls back to
+// ncclReduceScatter).
 // A rank accumulates a contiguous range of z planes, so in every shell the pixels it touched lie in a band of
 // latitudes -- a contiguous interval of RING indices -- and most of its [n_nu][npix] stack is zero.  NCCL's
 // reduce-scatter moves (P-1)/P of the whole stack per rank regardless.  Instead: (1) every rank measures the

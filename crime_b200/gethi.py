@@ -254,6 +254,28 @@ class GetHI:
         self._check(self.lib.gh_cuda_accumulate_audit(self._ctx, float(eps_scale), _ptr(cnt)))
         return dict(out=int(cnt[0]), inside=int(cnt[1]), unsure=int(cnt[2]), wrong=int(cnt[3]))
 
+    # -- point sources ---------------------------------------------------------------
+    def get_point_sources(self, ps) -> int:
+        """src/grid_tools.c:24-101: Poisson-sample the sources of every cell from the Gaussian density (between
+        create_d_and_vr_fields and get_HI).  `ps` is an abi.GhCudaPsourcesParams.  Returns the total over all ranks."""
+        n = C.c_longlong()
+        self._check(self.lib.gh_cuda_get_point_sources(self._ctx, C.byref(ps), C.byref(n)))
+        return n.value
+
+    def mk_psources_maps(self) -> np.ndarray:
+        """src/pixelize.c:58-148 (after get_HI): this rank's shells of maps_PS, mK."""
+        out = np.zeros((self.n_shells_here, self.npix), np.float32)
+        self._check(self.lib.gh_cuda_mk_psources_maps(self._ctx, _ptr(out)))
+        return out
+
+    def download_point_sources(self):
+        """(source counts, Poisson means) of this rank's slab, [nz_here][N][N]."""
+        n = self.n_grid
+        ns = np.zeros((self.nz_here, n, n), np.int32)
+        lam = np.zeros((self.nz_here, n, n), np.float32)
+        self._check(self.lib.gh_cuda_download_point_sources(self._ctx, _ptr(ns), _ptr(lam)))
+        return ns, lam
+
     # -- JoinT ingestion (SURVEY 8f-4) -----------------------------------------------------------
     def jt_merge_maps(self, components, nside_out: int, scale=None) -> np.ndarray:
         """merge_maps (src/main_jt.c:98-211) for this rank's shells: `components` is the list of component stacks in

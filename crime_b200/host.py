@@ -62,6 +62,24 @@ def read_run_params(fname, with_device: bool = False) -> dict:
     return d
 
 
+def psources_tables(fname) -> dict:
+    """setup_psources (host/psources.c, reference src/psources.c:98-131) for a parameter file: the redshift tables of
+    the reference plus the tabulated user functions that cross the C-ABI, as numpy arrays."""
+    L = lib()
+    L.gh_inspect_psources.argtypes = [C.c_void_p, C.POINTER(abi.GhCudaPsourcesParams)]
+    par = L.read_run_params_ex(str(fname).encode(), 0)
+    ps = abi.GhCudaPsourcesParams()
+    L.gh_inspect_psources(par, C.byref(ps))
+    as_np = lambda ptr, n: np.ctypeslib.as_array(ptr, shape=(n,)).copy()
+    d = dict(nz_arr=as_np(ps.nz_arr, ps.nz), bias_arr=as_np(ps.bias_arr, ps.nz), lcdf=as_np(ps.lcdf, ps.nz * (ps.nl + 1)),
+             sed_arr=as_np(ps.sed_arr, ps.nsed), z_max=ps.z_max, logl_min=ps.logl_min, logl_max=ps.logl_max, lognu_min=ps.lognu_min,
+             lognu_max=ps.lognu_max, hhub=ps.hhub)
+    n = C.c_int()
+    d["max_Lpdf_arr"] = as_np(L.gh_param_table(par, b"max_Lpdf_arr", C.byref(n)), n.value)
+    L.param_gethi_free(par)
+    return d
+
+
 def write_healpix_map(path, m: np.ndarray, nside: int) -> int:
     a = np.ascontiguousarray(m, dtype=np.float32)
     return lib().gh_write_healpix_map(a.ctypes.data_as(C.c_void_p), nside, str(path).encode())

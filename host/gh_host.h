@@ -21,6 +21,7 @@ extern "C" {
 #define GH_NZ 5001     /* reference NZ, src/common_gh.h:34 */
 #define GH_DZ 0.001    /* reference DZ, src/common_gh.h:33 */
 #define GH_NU_21 1420.40575177
+#define GH_NZ_PSOURCES 256 /* reference NZ_PSOURCES, src/common_gh.h:35 */
 
 /* The run state.  Field names follow ParamGetHI (src/common_gh.h:138-209) where they carry the same
  * meaning; device buffers live behind `cuda`, so there are no host grid pointers to free. */
@@ -50,6 +51,12 @@ typedef struct ParamGetHI {
   char prefixOut[256];
   double pos_obs[3];
   int do_psources;
+  /* point sources (src/common_gh.h:111-116 + the tabulated user functions that cross the C-ABI, host/psources.c) */
+  double glob_dz, glob_inv_dz;
+  double nz_psources_arr[GH_NZ_PSOURCES], max_Lpdf_arr[GH_NZ_PSOURCES], ps_bias_arr[GH_NZ_PSOURCES];
+  double *ps_lcdf, *ps_sed;
+  double ps_lognu_min, ps_lognu_max;
+  float *maps_PS; /* this rank's shells of the point-source maps, page-locked */
   double sigma2_gauss, mean_gauss;
   /* this rank's shells of the finished map stack, [n_shells_here][12 n_side^2], page-locked */
   float *maps_HI;
@@ -92,6 +99,15 @@ void get_HI(ParamGetHI *par);
 void mk_T_maps(ParamGetHI *par);
 void mk_T_maps_begin(ParamGetHI *par); /* non-blocking form; write_maps then overlaps the download */
 void end_fftw(ParamGetHI *par);
+
+/* src/psources.c, src/grid_tools.c:24-101, src/pixelize.c:58-148 (do_psources = 1) */
+void setup_psources(ParamGetHI *par);
+void get_point_sources(ParamGetHI *par);
+void mk_psources_maps(ParamGetHI *par);
+double n_of_z_psources(const ParamGetHI *par, double z);
+double bias_psources(double z);
+double temp_of_l(const ParamGetHI *par, double L0, double nu_obs, double z, double r, double dOmega);
+void gh_fill_psources_params(const ParamGetHI *par, gh_cuda_psources_params *out);
 
 /* helpers */
 void gh_fill_cuda_params(const ParamGetHI *par, gh_cuda_params *out);

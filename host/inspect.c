@@ -27,6 +27,7 @@ const double *gh_param_table(const ParamGetHI *p, const char *name, int *len)
   T("z_arr_r2z", p->z_arr_r2z, GH_NZ) T("r_arr_r2z", p->r_arr_r2z, GH_NZ)
   T("growth_d_arr", p->growth_d_arr, GH_NZ) T("growth_v_arr", p->growth_v_arr, GH_NZ)
   T("frac_HI_arr", p->frac_HI_arr, GH_NZ) T("bias_HI_arr", p->bias_HI_arr, GH_NZ)
+  T("nz_psources_arr", p->nz_psources_arr, GH_NZ_PSOURCES) T("max_Lpdf_arr", p->max_Lpdf_arr, GH_NZ_PSOURCES)
   T("nu0_arr", p->nu0_arr, p->nu0_arr ? p->n_nu : 0) T("nuf_arr", p->nuf_arr, p->nuf_arr ? p->n_nu : 0)
 #undef T
   *len = 0;
@@ -35,3 +36,10 @@ const double *gh_param_table(const ParamGetHI *p, const char *name, int *len)
 
 const float *gh_param_maps(const ParamGetHI *p) { return p->maps_HI; }
 const char *gh_param_prefix(const ParamGetHI *p) { return p->prefixOut; }
+
+/* setup_psources on a parsed parameter set, and the block that crosses the C-ABI (valid while `p` lives) */
+void gh_inspect_psources(ParamGetHI *p, gh_cuda_psources_params *out)
+{
+  setup_psources(p);
+  gh_fill_psources_params(p, out);
+}

@@ -100,7 +100,6 @@ ParamGetHI *read_run_params_ex(const char *fname, int with_device)
   par->irregular_nutable = have_nutable;
   if (have_nutable) read_nutable(par);
   else { par->nu_min = nu_min_key; par->nu_max = nu_max_key; par->n_nu = n_nu_key; }
-  if (par->do_psources) report_error(1, "do_psources=1 is not part of the GPU hot path (the reference README discourages it)\n");
   gh_phase("parameter file");
   cosmo_set(par);
   gh_phase("cosmo_set");
@@ -262,6 +261,17 @@ void write_maps(ParamGetHI *par)
                  ms[GH_T_MAPS] + ms[GH_T_REDUCE] + ms[GH_T_D2H]);
     par->maps_streaming = 0;
   }
+  if (par->do_psources && par->maps_PS) { /* src/io_gh.c:122-128 */
+    print_info("*** Writing single slice files %s_ps_###.fits\n", par->prefixOut);
+#pragma omp parallel for schedule(dynamic) reduction(+ : n_exist, n_fail)
+    for (int s = 0; s < par->n_shells_here; s++) {
+      char fn[300];
+      snprintf(fn, sizeof(fn), "%s_ps_%03d.fits", par->prefixOut, par->shell0_here + s + 1);
+      const int rc = gh_write_healpix_map(par->maps_PS + (size_t)s * npix, par->n_side, fn);
+      if (rc == 1) n_exist++;
+      else if (rc) n_fail++;
+    }
+  }
   if (n_exist) report_error(0, "%d of the %s_###.fits files exist and were left untouched\n", n_exist, par->prefixOut);
   if (n_fail) report_error(1, "could not write %d of the %s_###.fits files\n", n_fail, par->prefixOut);
 }
@@ -269,7 +279,8 @@ void write_maps(ParamGetHI *par)
 void param_gethi_free(ParamGetHI *par)
 {
   if (!par) return;
+  if (par->maps_PS) gh_cuda_host_free(par->maps_PS);
   end_fftw(par);
-  free(par->logkarr); free(par->pkarr); free(par->nu0_arr); free(par->nuf_arr);
+  free(par->logkarr); free(par->pkarr); free(par->nu0_arr); free(par->nuf_arr); free(par->ps_lcdf); free(par->ps_sed);
   free(par);
 }

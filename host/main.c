@@ -27,9 +27,18 @@ static int run_rank(const char *fname, int rank, int nranks, int device, const v
   gh_phase("run-parameter banner");
   print_info("Seed : %u\n", par->seed_rng);
   create_d_and_vr_fields(par);
+  if (par->do_psources) { /* src/main_gh.c:55-59: Poisson-sample the sources from the Gaussian field, before get_HI */
+    setup_psources(par);
+    get_point_sources(par);
+  }
   get_HI(par);
   gh_phase("create_d_and_vr_fields + get_HI");
-  mk_T_maps_begin(par); /* non-blocking mk_T_maps ... */
+  if (par->do_psources) { /* the source maps are needed before the writers start: blocking form, then src/main_gh.c:64-65 */
+    mk_T_maps(par);
+    mk_psources_maps(par);
+  } else {
+    mk_T_maps_begin(par); /* non-blocking mk_T_maps ... */
+  }
   write_maps(par);      /* ... every rank writes the shells it owns as they arrive from the device */
   gh_phase("mk_T_maps + write_maps");
   if (NodeThis == 0) timer(5);

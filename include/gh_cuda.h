@@ -224,6 +224,33 @@ int gh_cuda_stage_times(gh_cuda_ctx *ctx, double *ms_out);
  * z_ms[0] = density, z_ms[1] = velocity potential; -1 when off. */
 int gh_cuda_fft_pass_times(gh_cuda_ctx *ctx, double *z_ms);
 
+/* ---- point sources on the same grids (do_psources = 1) ----
+ * What setup_psources (src/psources.c:98-131) leaves in ParamGetHI, plus host-side tabulations of the three
+ * user-definable functions of src/psources.c:33-71 (l_z_function through its cumulative distribution, spec_ed,
+ * bias_psources), so that editing them stays a host-side change.  All pointers are HOST pointers. */
+typedef struct gh_cuda_psources_params {
+  int nz;                 /* NZ_PSOURCES: redshift bins of width z_max / nz (src/psources.c:106) */
+  double z_max;           /* par->z_max */
+  const double *nz_arr;   /* [nz] nz_psources_arr: sources per (Mpc/h)^3 integrated over luminosities */
+  const double *bias_arr; /* [nz] bias_psources(z_i) */
+  int nl;                 /* luminosity bins of the tabulated distribution */
+  double logl_min, logl_max;  /* LLOGMIN, LLOGMAX (src/psources.c:25-26), log10 of L / 10^22 W/Hz */
+  const double *lcdf;     /* [nz][nl + 1] cumulative P(log10 L | z_i): 0 at logl_min, 1 at logl_max */
+  int nsed;               /* spec_ed on nsed points uniform in log10(nu / MHz) over [lognu_min, lognu_max] */
+  double lognu_min, lognu_max;
+  const double *sed_arr;  /* [nsed] */
+  double hhub;
+} gh_cuda_psources_params;
+/* get_point_sources (src/grid_tools.c:24-101): Poisson-samples the number of sources of every cell from the Gaussian
+ * density field -- call it between gh_cuda_create_d_and_vr_fields and gh_cuda_get_HI, as main_gh.c:55-59 does.
+ * np_total_out: sources in the whole box (all ranks). */
+int gh_cuda_get_point_sources(gh_cuda_ctx *ctx, const gh_cuda_psources_params *ps, long long *np_total_out);
+/* mk_psources_maps (src/pixelize.c:58-148): call after gh_cuda_get_HI (it reads Delta z_RSD).  maps_ps_host receives
+ * this rank's shells [n_shells_here][npix] of maps_PS in mK (may be NULL). */
+int gh_cuda_mk_psources_maps(gh_cuda_ctx *ctx, float *maps_ps_host);
+/* test aid: this rank's slab of source counts [nz_here][N][N] and of the Poisson means they were drawn from */
+int gh_cuda_download_point_sources(gh_cuda_ctx *ctx, int *nsources_out, float *lambda_out);
+
 /* ---- JoinT ingestion of GetHI output on the device ----
  * gh_cuda_jt_merge_maps replaces merge_maps (src/main_jt.c:98-211) for the shells this rank owns: for every shell,
  * map_in = 0, then the n_comp components are added in the order given (the reference's order: cosmological signal,

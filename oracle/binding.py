@@ -238,6 +238,21 @@ class Reference:
     TABLES = ("logkarr", "pkarr", "z_arr_z2r", "r_arr_z2r", "z_arr_r2z", "r_arr_r2z", "growth_d_arr",
               "growth_v_arr", "nu0_arr", "nuf_arr")
 
+    # -- point sources (do_psources = 1) --
+    def nsources(self, par, n_grid: int) -> np.ndarray:
+        """nsources as get_point_sources left it, [N][N][N] (the reference indexes it with the padded pitch)."""
+        ngx = 2 * (n_grid // 2 + 1)
+        a = np.ctypeslib.as_array(self.lib.ref_nsources(par), shape=(n_grid, n_grid, ngx))
+        return a[:, :, :n_grid].copy()
+
+    def maps_PS(self, par, n_nu: int, npix: int) -> np.ndarray:
+        return np.ctypeslib.as_array(self.lib.ref_maps_PS(par), shape=(n_nu, npix)).copy()
+
+    def draw_luminosity(self, par, z: float, n: int, seed: int = 7) -> np.ndarray:
+        out = np.zeros(n)
+        self.lib.ref_draw_luminosity(par, z, seed, n, out.ctypes.data_as(_vp))
+        return out
+
     @staticmethod
     def available(regular: bool = False) -> bool:
         return (REF_SO_REGULAR if regular else REF_SO).exists()
@@ -269,6 +284,20 @@ class Reference:
         lib.ref_grid.argtypes = [_vp, C.c_char_p]
         lib.ref_grid.restype = C.POINTER(C.c_float)
         lib.ref_set_fft_io.argtypes = [_vp, _vp, _vp, _vp]
+        for n in ("ref_setup_psources", "ref_get_point_sources", "ref_mk_psources_maps"):
+            getattr(lib, n).argtypes = [_vp]
+            getattr(lib, n).restype = None
+        lib.ref_scale_psources.argtypes = [_vp, _d]
+        lib.ref_n_of_z_psources.argtypes = [_vp, _d]
+        lib.ref_n_of_z_psources.restype = _d
+        lib.ref_temp_of_l.argtypes = [_vp, _d, _d, _d, _d, _d]
+        lib.ref_temp_of_l.restype = _d
+        lib.ref_draw_luminosity.argtypes = [_vp, _d, C.c_uint, _i, _vp]
+        lib.ref_draw_luminosity.restype = _d
+        lib.ref_nsources.argtypes = [_vp]
+        lib.ref_nsources.restype = C.POINTER(C.c_int)
+        lib.ref_maps_PS.argtypes = [_vp]
+        lib.ref_maps_PS.restype = C.POINTER(C.c_float)
 
     def read_run_params(self, fname: str):
         """The reference's -D_DEBUG cosmo_set dumps test_cosmo.dat into the current directory: run it from a

@@ -27,6 +27,30 @@ double ref_vgrowth_of_r(void *p, double r) { return vgrowth_of_r((ParamGetHI *)p
 double ref_fraction_HI(double z) { return fraction_HI(z); }
 double ref_bias_HI(double z) { return bias_HI(z); }
 
+/* ---- point sources (do_psources = 1): the reference's own functions, plus a density rescaling for tests ---- */
+void ref_setup_psources(void *p) { setup_psources((ParamGetHI *)p); }
+void ref_get_point_sources(void *p) { get_point_sources((ParamGetHI *)p); }
+void ref_mk_psources_maps(void *p) { mk_psources_maps((ParamGetHI *)p); }
+double ref_n_of_z_psources(void *p, double z) { return n_of_z_psources((ParamGetHI *)p, z); }
+double ref_temp_of_l(void *p, double l0, double nu, double z, double r, double domega) { return temp_of_l((ParamGetHI *)p, l0, nu, z, r, domega); }
+double ref_draw_luminosity(void *p, double z, unsigned int seed, int n, double *out)
+{
+  gsl_rng *rng = init_rng(seed);
+  double sum = 0;
+  for (int i = 0; i < n; i++) { out[i] = draw_luminosity((ParamGetHI *)p, z, rng); sum += out[i]; }
+  end_rng(rng);
+  return sum;
+}
+/* thin the catalogue by f: n(z) -> f n(z); the rejection envelope max_Lpdf = 1.1 max / n(z) scales by 1/f so that
+ * draw_luminosity's distribution stays what it was (l_distribution divides by n_of_z_psources) */
+void ref_scale_psources(void *vp, double f)
+{
+  ParamGetHI *p = (ParamGetHI *)vp;
+  for (int i = 0; i < NZ_PSOURCES; i++) { p->nz_psources_arr[i] *= f; p->max_Lpdf_arr[i] /= f; }
+}
+int *ref_nsources(void *vp) { return ((ParamGetHI *)vp)->nsources; }
+float *ref_maps_PS(void *vp) { return (float *)((ParamGetHI *)vp)->maps_PS; }
+
 double ref_get_double(void *vp, const char *name)
 {
   ParamGetHI *p = (ParamGetHI *)vp;
@@ -62,6 +86,7 @@ const double *ref_get_table(void *vp, const char *name, int *len)
   T("z_arr_z2r", p->z_arr_z2r, NZ) T("r_arr_z2r", p->r_arr_z2r, NZ)
   T("z_arr_r2z", p->z_arr_r2z, NZ) T("r_arr_r2z", p->r_arr_r2z, NZ)
   T("growth_d_arr", p->growth_d_arr, NZ) T("growth_v_arr", p->growth_v_arr, NZ)
+  T("nz_psources_arr", p->nz_psources_arr, NZ_PSOURCES) T("max_Lpdf_arr", p->max_Lpdf_arr, NZ_PSOURCES)
 #ifdef _IRREGULAR_NUTABLE
   T("nu0_arr", p->nu0_arr, p->n_nu) T("nuf_arr", p->nuf_arr, p->n_nu)
 #endif

@@ -32,11 +32,25 @@ void gsl_rng_free(gsl_rng *r) { free(r); }
 
 unsigned int gsl_ran_poisson(gsl_rng *r, double mu)
 {
-  /* link-only on the GetHI path with do_psources=0; simple multiplication method for completeness */
-  double L = exp(-mu), p = 1.0;
-  unsigned int k = 0;
-  do { k++; p *= gsl_rng_uniform(r); } while (p > L);
-  return k - 1;
+  /* stand-in for GSL's sampler (same distribution, different stream): multiplication method for small means,
+   * Hoermann's PTRS transformed rejection above (Insurance: Mathematics and Economics 12 (1993) 39) */
+  if (!(mu > 0)) return 0;
+  if (mu < 12.0) {
+    double L = exp(-mu), p = 1.0;
+    unsigned int k = 0;
+    do { k++; p *= gsl_rng_uniform(r); } while (p > L);
+    return k - 1;
+  }
+  const double slam = sqrt(mu), loglam = log(mu), b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+  const double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2);
+  for (;;) {
+    const double U = gsl_rng_uniform(r) - 0.5, V = gsl_rng_uniform(r);
+    const double us = 0.5 - fabs(U);
+    const double k = floor((2 * a / us + b) * U + mu + 0.43);
+    if (us >= 0.07 && V <= vr) return (unsigned int)k;
+    if (k < 0 || (us < 0.013 && V > us)) continue;
+    if (log(V) + log(invalpha) - log(a / (us * us) + b) <= -mu + k * loglam - lgamma(k + 1)) return (unsigned int)k;
+  }
 }
 
 gsl_error_handler_t *gsl_set_error_handler_off(void) { return NULL; }

@@ -15,23 +15,22 @@ def _ngpu():
 
 
 # bounds: GH_MAP_BOUNDS, forced plane ranges for the map accumulation (None = the cost model's; "off" = own slabs;
-# "sparse" = the cost model's ranges and GH_SPARSE_REDUCE=1).
+# "nccl" = the cost model's ranges with GH_NO_SPARSE_REDUCE=1: ncclReduceScatter instead of the default sparse map reduction
+# over peer memory).
 # The forced cases make rank 0 pull planes from above, rank 1 from below, in more than one staging chunk, and
 # leave one rank without any of its own planes.
 @pytest.mark.parametrize("world,n_grid,n_side,bounds", [(2, 64, 32, None), (2, 64, 32, "57"), (2, 64, 32, "9"), (2, 64, 32, "off"),
                                                         (4, 128, 64, None), (4, 128, 64, "70,75,80"), (8, 128, 64, None),
-                                                        (2, 64, 32, "sparse"), (4, 128, 64, "sparse"), (8, 128, 64, "sparse")])
+                                                        (2, 64, 32, "nccl"), (4, 128, 64, "nccl"), (8, 128, 64, "nccl")])
 def test_slab_decomposition_matches_single_gpu(world, n_grid, n_side, bounds):
     import os
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
-    if bounds == "sparse" and not os.environ.get("GH_TEST_EXPERIMENTAL"):
-        pytest.skip("GH_SPARSE_REDUCE has not been run on hardware yet: GH_TEST_EXPERIMENTAL=1")
     env = dict(os.environ)
     if bounds == "off":
         env["GH_NO_REBALANCE"] = "1"
-    elif bounds == "sparse":  # opt-in map reduction over peer memory instead of ncclReduceScatter
-        env["GH_SPARSE_REDUCE"] = "1"
+    elif bounds == "nccl":  # the NCCL collective instead of the sparse map reduction over peer memory
+        env["GH_NO_SPARSE_REDUCE"] = "1"
     elif bounds:
         env["GH_MAP_BOUNDS"] = bounds
     _run_worker(world, n_grid, n_side, "full", env, f"{world}gpu_{n_grid}_{bounds or 'model'}")

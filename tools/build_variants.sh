@@ -9,7 +9,7 @@ NVF="$ARCH -O3 -std=c++17 -lineinfo -Xcompiler -fPIC"
 while [ $# -ge 2 ]; do
   name=$1; flags=$2; shift 2
   d=variants/$name; mkdir -p $d
-  for f in gh_api gh_fft gh_kgen gh_fields gh_joint; do nvcc $NVF $flags -c $f.cu -o $d/$f.o & done
+  for f in gh_api gh_fft gh_kgen gh_fields gh_joint gh_psources; do nvcc $NVF $flags -c $f.cu -o $d/$f.o & done
   nvcc $NVF -fmad=false $flags -c gh_pixelize.cu -o $d/gh_pixelize.o &
   wait
   nvcc $ARCH -shared -o variants/libgh_cuda_$name.so $d/*.o -lnccl
