@@ -425,16 +425,120 @@ static int setup_map_peers(gh_cuda_ctx *c)
   return 0;
 }
 
+// Collective: map `mine` (a cudaMalloc'ed buffer, or nullptr when this rank could not allocate one) on every peer.
+// ok_out is the agreement of all ranks (min over "I have a buffer and mapped everybody's").
+static int exchange_ipc(gh_cuda_ctx *c, void *mine_ptr, void **peers_out, bool *ok_out)
+{
+  const int P = c->d.nranks, me = c->d.rank;
+  const size_t hsz = sizeof(cudaIpcMemHandle_t);
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  bool ok = mine_ptr != nullptr && cudaIpcGetMemHandle(&mine, mine_ptr) == cudaSuccess;
+  // a first agreement: nobody opens handles unless everybody has one
+  int flag = ok ? 1 : 0;
+  GH_CUDA_OK(cudaMemcpyAsync(c->d_barrier, &flag, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  GH_NCCL_OK(ncclAllReduce(c->d_barrier, c->d_barrier, 1, ncclInt, ncclMin, c->comm, c->stream));
+  GH_CUDA_OK(cudaMemcpyAsync(&flag, c->d_barrier, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  GH_CUDA_OK(cudaStreamSynchronize(c->stream));
+  GH_CUDA_OK(cudaMemsetAsync(c->d_barrier, 0, sizeof(int), c->stream));
+  cudaGetLastError();
+  *ok_out = false;
+  if (flag != 1) return 0;
+  char *d_all = nullptr;
+  GH_CUDA_OK(cudaMalloc(&d_all, hsz * P));
+  GH_CUDA_OK(cudaMemcpyAsync(d_all + hsz * me, &mine, hsz, cudaMemcpyHostToDevice, c->stream));
+  GH_NCCL_OK(ncclAllGather(d_all + hsz * me, d_all, hsz, ncclChar, c->comm, c->stream));
+  cudaIpcMemHandle_t *all = (cudaIpcMemHandle_t *)malloc(hsz * P);
+  GH_REQUIRE(all, "out of host memory");
+  cudaError_t e = cudaMemcpyAsync(all, d_all, hsz * P, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d_all);
+  if (e != cudaSuccess) { free(all); gh_set_error("IPC handle exchange failed: %s", cudaGetErrorString(e)); return 1; }
+  for (int q = 0; q < P && ok; ++q) {
+    if (q == me) { peers_out[q] = mine_ptr; continue; }
+    void *pm = nullptr;
+    if (cudaIpcOpenMemHandle(&pm, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = false;
+    else peers_out[q] = pm;
+  }
+  free(all);
+  cudaGetLastError();
+  flag = ok ? 1 : 0;
+  GH_CUDA_OK(cudaMemcpyAsync(c->d_barrier, &flag, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  GH_NCCL_OK(ncclAllReduce(c->d_barrier, c->d_barrier, 1, ncclInt, ncclMin, c->comm, c->stream));
+  GH_CUDA_OK(cudaMemcpyAsync(&flag, c->d_barrier, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  GH_CUDA_OK(cudaStreamSynchronize(c->stream));
+  GH_CUDA_OK(cudaMemsetAsync(c->d_barrier, 0, sizeof(int), c->stream));
+  if (flag != 1) {
+    for (int q = 0; q < P; ++q) {
+      if (q != me && peers_out[q]) cudaIpcCloseMemHandle(peers_out[q]);
+      peers_out[q] = nullptr;
+    }
+    cudaGetLastError();
+    return 0;
+  }
+  *ok_out = true;
+  return 0;
+}
+
+// Streams, events and the second receive buffer of the copy-engine transposes (fft_both_fields_ce, gh_fft.cu)
+static int setup_ce_transpose(gh_cuda_ctx *c)
+{
+  const GhDev &d = c->d;
+  c->ce_transpose = getenv("GH_FUSED_TRANSPOSE") == nullptr;
+  if (!c->ce_transpose) return 0;
+  for (int k = 0; k < GH_N_COPY_STREAMS; ++k) GH_CUDA_OK(cudaStreamCreateWithFlags(&c->ce_stream[k], cudaStreamNonBlocking));
+  for (int f = 0; f < 2; ++f) {
+    GH_CUDA_OK(cudaEventCreateWithFlags(&c->ev_z[f], cudaEventDisableTiming));
+    GH_CUDA_OK(cudaEventCreateWithFlags(&c->ev_free[f], cudaEventDisableTiming));
+    for (int k = 0; k < GH_N_COPY_STREAMS; ++k) GH_CUDA_OK(cudaEventCreateWithFlags(&c->ev_sent[f][k], cudaEventDisableTiming));
+  }
+  const size_t slab_bytes = c->slab_complex * sizeof(float2);
+  const size_t maps_bytes = (size_t)d.n_nu_pad * d.npix * sizeof(float);
+  if (getenv("GH_ONE_RECV_BUFFER")) return 0;  // test hook: the single-buffer sequence
+  if (c->sparse_reduce && maps_bytes >= slab_bytes && !getenv("GH_OWN_RECV_BUFFER")) {
+    // the map accumulation stack is idle during the FFTs and already mapped on every peer
+    c->recv2 = reinterpret_cast<float2 *>(c->maps);
+    for (int q = 0; q < d.nranks; ++q) c->recv2_peers[q] = reinterpret_cast<float2 *>(c->map_peers[q]);
+    return 0;
+  }
+  size_t free_b = 0, total_b = 0;
+  GH_CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+  void *buf = nullptr;
+  if (free_b > slab_bytes + total_b / 8 && cudaMalloc(&buf, slab_bytes) != cudaSuccess) buf = nullptr;
+  cudaGetLastError();
+  bool ok = false;
+  void *peers[GH_MAX_RANKS] = {nullptr};
+  if (exchange_ipc(c, buf, peers, &ok)) return 1;
+  if (!ok) { if (buf) cudaFree(buf); return 0; }
+  c->recv2 = (float2 *)buf;
+  c->recv2_owned = true;
+  for (int q = 0; q < d.nranks; ++q) c->recv2_peers[q] = (float2 *)peers[q];
+  return 0;
+}
+
 extern "C" int gh_cuda_destroy(gh_cuda_ctx *c)
 {
   if (!c) return 0;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   gh_psources_release(c);
+  for (int k = 0; k < GH_N_COPY_STREAMS; ++k)
+    if (c->ce_stream[k]) { cudaStreamSynchronize(c->ce_stream[k]); cudaStreamDestroy(c->ce_stream[k]); c->ce_stream[k] = nullptr; }
+  for (int f = 0; f < 2; ++f) {
+    if (c->ev_z[f]) cudaEventDestroy(c->ev_z[f]);
+    if (c->ev_free[f]) cudaEventDestroy(c->ev_free[f]);
+    for (int k = 0; k < GH_N_COPY_STREAMS; ++k)
+      if (c->ev_sent[f][k]) cudaEventDestroy(c->ev_sent[f][k]);
+  }
   if (c->have_comm && c->d_barrier) {
     // nobody may free a slab a peer could still be reading
     ncclAllReduce(c->d_barrier, c->d_barrier, 1, ncclInt, ncclSum, c->comm, c->stream);
     cudaStreamSynchronize(c->stream);
+  }
+  if (c->recv2_owned) {
+    for (int q = 0; q < c->d.nranks && q < GH_MAX_RANKS; ++q)
+      if (q != c->d.rank && c->recv2_peers[q]) cudaIpcCloseMemHandle(c->recv2_peers[q]);
+    cudaFree(c->recv2);
   }
   for (int q = 0; q < c->d.nranks && q < GH_MAX_RANKS; ++q) {
     if (q == c->d.rank) continue;
@@ -617,6 +721,7 @@ extern "C" int gh_cuda_create(const gh_cuda_params *p, int rank, int nranks, con
     // sparse map reduction over peer memory: validated against the single-GPU run on 2 and 4 GPUs and 1.9x faster than
     // ncclReduceScatter there (profiles/r2/); GH_NO_SPARSE_REDUCE=1 restores the NCCL collective
     if (c->have_peers && !getenv("GH_NO_SPARSE_REDUCE") && setup_map_peers(c)) { gh_cuda_destroy(c); return 1; }
+    if (c->have_peers && setup_ce_transpose(c)) { gh_cuda_destroy(c); return 1; }
   }
   CREATE_OK(cudaStreamSynchronize(c->stream));
 #undef CREATE_OK
@@ -722,8 +827,7 @@ extern "C" int gh_cuda_fft_fields(gh_cuda_ctx *c)
   c->fft_stats_blocks = 0;
   c->sigma_ready = false;
   StageTimer t(c, GH_T_FFT);
-  if (gh_launch_fft_field(c, c->gridA)) return 1;  // src/fourier.c:391
-  return gh_launch_fft_field(c, c->gridB);         // src/fourier.c:392
+  return gh_launch_fft_both_fields(c);  // src/fourier.c:391-392
 }
 
 extern "C" int gh_cuda_radial_velocity(gh_cuda_ctx *c)

@@ -557,42 +557,47 @@ int launch_rows(gh_cuda_ctx *c, float2 *data, long long nrows, float norm, long 
   return 0;
 }
 
+// (1) z axis, local because k-space is ky-distributed: all nky_here*nh columns as one flat group.
+// peer_store: the last radix pass stores every output plane straight into the owning rank's receive buffer (the
+// transpose fused into the pass); otherwise in place, which leaves block q (the kz planes of rank q's z slab)
+// contiguous in the slab, ready to be shipped as one piece.
 template <int N, int WSEL = 0, int NTSEL = 0>
-int fft_field(gh_cuda_ctx *c, float2 *field)
+int fft_z_pass(gh_cuda_ctx *c, float2 *field, bool peer_store)
+{
+  const GhDev &d = c->d;
+  using Cfg = FftCfg<N, WSEL, NTSEL>;
+  const int nh = d.nh;
+  StridedGeom g;
+  g.lines_per_group = d.nky_here * nh;
+  g.tiles_per_group = (g.lines_per_group + Cfg::W - 1) / Cfg::W;
+  g.src_group_stride = g.dst_group_stride = 0;
+  g.src_stride = g.dst_stride = (long long)d.nky_here * nh;
+  g.grp0 = 0;
+  g.blk_shift = 30;
+  g.src_chunk = 0;
+  g.peer_mode = peer_store ? 1 : 0;
+  g.nz_peer = d.nz_here;
+  g.me = d.rank;
+  g.peer_chunk = (long long)d.nz_here * d.nky_here * nh;
+  const int mi = (field == c->gridA) ? 0 : 1;
+  TmaGeom tg;
+  tg.box_rows = N < 256 ? N : 256; tg.nchunks = 1; tg.nh = nh;
+  if (c->fft_tma && (field == c->gridA || field == c->gridB) && !c->fft_map_ok[mi])
+    c->fft_map_ok[mi] = make_map_z(&c->fft_map[mi], field, g.lines_per_group, N, Cfg::WT, tg.box_rows);
+  if (c->fft_tma && (field == c->gridA || field == c->gridB) && c->fft_map_ok[mi])
+    return launch_strided_tma<N, false>(c, c->fft_map[mi], c->fft_map[mi], field, g, tg, 1);
+  return launch_strided<N, WSEL, NTSEL>(c, field, field, g, 1);
+}
+
+// (3) y axis per z plane, (4) x axis half-complex -> real with the normalisation fused.  ysrc: the field itself on
+// one rank, a transpose receive buffer [q][z_local][ky_local][kx] (ky = q*nky_here + ky_local) on several.
+template <int N, int WSEL = 0, int NTSEL = 0>
+int fft_yx_passes(gh_cuda_ctx *c, float2 *field, const float2 *ysrc)
 {
   const GhDev &d = c->d;
   using Cfg = FftCfg<N, WSEL, NTSEL>;
   const int nh = d.nh;
   const double normd = pow(sqrt(2.0 * 3.14159265358979323846) / d.l_box, 3.0);  // src/fourier.c:403
-  // (1) z axis, local because k-space is ky-distributed: all nky_here*nh columns as one flat group
-  {
-    StridedGeom g;
-    g.lines_per_group = d.nky_here * nh;
-    g.tiles_per_group = (g.lines_per_group + Cfg::W - 1) / Cfg::W;
-    g.src_group_stride = g.dst_group_stride = 0;
-    g.src_stride = g.dst_stride = (long long)d.nky_here * nh;
-    g.grp0 = 0;
-    g.blk_shift = 30;
-    g.src_chunk = 0;
-    g.peer_mode = (d.nranks > 1 && c->have_peers) ? 1 : 0;
-    g.nz_peer = d.nz_here;
-    g.me = d.rank;
-    g.peer_chunk = (long long)d.nz_here * d.nky_here * nh;
-    // peers must be done with their receive buffers (previous field's y pass, previous realisation's maps)
-    if (g.peer_mode && gh_stream_barrier(c)) return 1;
-    if (c->time_fft_passes) cudaEventRecord(c->ev_pass[field == c->gridA ? 0 : 1][0], c->stream);
-    const int mi = (field == c->gridA) ? 0 : 1;
-    TmaGeom tg;
-    tg.box_rows = N < 256 ? N : 256; tg.nchunks = 1; tg.nh = nh;
-    if (c->fft_tma && (field == c->gridA || field == c->gridB) && !c->fft_map_ok[mi])
-      c->fft_map_ok[mi] = make_map_z(&c->fft_map[mi], field, g.lines_per_group, N, Cfg::WT, tg.box_rows);
-    if (c->fft_tma && (field == c->gridA || field == c->gridB) && c->fft_map_ok[mi]) {
-      if (launch_strided_tma<N, false>(c, c->fft_map[mi], c->fft_map[mi], field, g, tg, 1)) return 1;
-    } else {
-      if (launch_strided<N, WSEL, NTSEL>(c, field, field, g, 1)) return 1;
-    }
-  }
-  const float2 *ysrc = field;
   StridedGeom g;
   g.peer_mode = 0; g.nz_peer = 1; g.me = 0; g.peer_chunk = 0;
   g.lines_per_group = nh;
@@ -600,43 +605,25 @@ int fft_field(gh_cuda_ctx *c, float2 *field)
   g.dst_group_stride = (long long)d.n * nh;
   g.dst_stride = nh;
   if (d.nranks > 1) {
-    // (2) the one transpose of this field: block q (kz in q's z slab) goes to rank q
-    const size_t chunk = (size_t)d.nz_here * d.nky_here * nh;
-    if (c->have_peers) {
-      // already done: the z pass stored its output into the peers' receive buffers; wait until all have
-      if (gh_stream_barrier(c)) return 1;
-    } else {
-      GH_NCCL_OK(ncclGroupStart());
-      for (int q = 0; q < d.nranks; ++q) {
-        GH_NCCL_OK(ncclSend(field + q * chunk, chunk * 2, ncclFloat, q, c->comm, c->stream));
-        GH_NCCL_OK(ncclRecv(c->gridC + q * chunk, chunk * 2, ncclFloat, q, c->comm, c->stream));
-      }
-      GH_NCCL_OK(ncclGroupEnd());
-    }
-    if (c->time_fft_passes) cudaEventRecord(c->ev_pass[field == c->gridA ? 0 : 1][1], c->stream);
-    // received layout [q][z_local][ky_local][kx]; ky = q*nky_here + ky_local
-    ysrc = c->gridC;
     g.src_group_stride = (long long)d.nky_here * nh;
     g.src_stride = nh;
     g.blk_shift = ilog2(d.nky_here);
-    g.src_chunk = (long long)chunk;
+    g.src_chunk = (long long)d.nz_here * d.nky_here * nh;
   } else {
-    if (c->time_fft_passes) cudaEventRecord(c->ev_pass[field == c->gridA ? 0 : 1][1], c->stream);
     g.src_group_stride = (long long)d.n * nh;
     g.src_stride = nh;
     g.blk_shift = 30;
     g.src_chunk = 0;
   }
-  // (3) y axis per z plane, (4) x axis half-complex -> real with the normalisation fused.  The two passes
-  // run over batches of planes small enough to stay in the 126 MB L2, so the x pass finds the y pass's
-  // output there: HBM sees one read and one write per mode for both passes together.
+  // The two passes can run over batches of planes small enough to stay in the 126 MB L2 (GH_FFT_BATCH_MB; measured: it
+  // does not pay on B200, off by default)
   const size_t plane_bytes = (size_t)d.n * nh * sizeof(float2);
   const size_t nb_sz = c->fft_batch_bytes / plane_bytes;
   const int nb = nb_sz < 1 ? 1 : (nb_sz > (size_t)d.nz_here ? d.nz_here : (int)nb_sz);
   for (int z0 = 0; z0 < d.nz_here; z0 += nb) {
     const int nz = (d.nz_here - z0 < nb) ? d.nz_here - z0 : nb;
     g.grp0 = z0;
-    // TMA-fed y pass: the source is this field's slab on one rank, the transpose receive buffer on several
+    // TMA-fed y pass
     const int mi = (field == c->gridA) ? 2 : 3;
     const int nchunks = d.nranks > 1 ? d.nranks : 1, rows_per_chunk = N / nchunks;
     TmaGeom tg;
@@ -658,11 +645,130 @@ int fft_field(gh_cuda_ctx *c, float2 *field)
   return 0;
 }
 
+// One field, start to finish (one rank; several ranks with the transpose fused into the z pass, or through NCCL when
+// the peers' buffers cannot be mapped).
+template <int N, int WSEL = 0, int NTSEL = 0>
+int fft_field(gh_cuda_ctx *c, float2 *field)
+{
+  const GhDev &d = c->d;
+  const int fi = field == c->gridA ? 0 : 1;
+  const bool fused = d.nranks > 1 && c->have_peers;
+  // peers must be done with their receive buffers (previous field's y pass, previous realisation's maps)
+  if (fused && gh_stream_barrier(c)) return 1;
+  if (c->time_fft_passes) cudaEventRecord(c->ev_pass[fi][0], c->stream);
+  if (fft_z_pass<N, WSEL, NTSEL>(c, field, fused)) return 1;
+  const float2 *ysrc = field;
+  if (d.nranks > 1) {
+    // (2) the one transpose of this field: block q (kz in q's z slab) goes to rank q
+    const size_t chunk = (size_t)d.nz_here * d.nky_here * d.nh;
+    if (fused) {
+      // already done: the z pass stored its output into the peers' receive buffers; wait until all have
+      if (gh_stream_barrier(c)) return 1;
+    } else {
+      GH_NCCL_OK(ncclGroupStart());
+      for (int q = 0; q < d.nranks; ++q) {
+        GH_NCCL_OK(ncclSend(field + q * chunk, chunk * 2, ncclFloat, q, c->comm, c->stream));
+        GH_NCCL_OK(ncclRecv(c->gridC + q * chunk, chunk * 2, ncclFloat, q, c->comm, c->stream));
+      }
+      GH_NCCL_OK(ncclGroupEnd());
+    }
+    ysrc = c->gridC;
+  }
+  if (c->time_fft_passes) cudaEventRecord(c->ev_pass[fi][1], c->stream);
+  return fft_yx_passes<N, WSEL, NTSEL>(c, field, ysrc);
+}
+
+// Both fields on several ranks with the transposes on the copy engines, pipelined against the compute passes:
+//   compute stream : barrier | z(A) | z(B)            | wait A, barrier | y(A) x(A) | wait B, barrier | y(B) x(B)
+//   copy streams   :         |      | A -> peers' C   | B -> peers' D   (NVLink, 1 large contiguous block per peer)
+// The in-place z pass leaves block q of the slab -- the kz planes rank q will own -- contiguous, so the all-to-all is
+// nranks - 1 plain peer copies of nz_here * nky_here * nh modes each (plus one local copy), which the copy engines move
+// at NVLink line rate without occupying an SM, while the SMs transform the other field.  D is a second receive
+// buffer: the (idle) map accumulation stack when it is large enough, else an extra slab when memory allows, else the
+// velocity potential's copies wait until every rank has consumed C (one more barrier, less overlap).
+// A barrier (1-int all-reduce) after a rank has waited for its own copies means all copies into every rank have landed.
+template <int N>
+int fft_both_fields_ce(gh_cuda_ctx *c)
+{
+  const GhDev &d = c->d;
+  const int P = d.nranks, me = d.rank;
+  const size_t chunk = (size_t)d.nz_here * d.nky_here * d.nh;
+  float2 *fields[2] = {c->gridA, c->gridB};
+  const bool two = c->recv2 != nullptr;
+  auto ship = [&](int fi) -> int {
+    // copy streams start after the z pass of this field (ev_z[fi]) and after the barrier that freed the destination
+    for (int k = 0; k < GH_N_COPY_STREAMS; ++k) {
+      GH_CUDA_OK(cudaStreamWaitEvent(c->ce_stream[k], c->ev_z[fi], 0));
+      GH_CUDA_OK(cudaStreamWaitEvent(c->ce_stream[k], c->ev_free[fi], 0));
+    }
+    if (c->time_fft_passes) GH_CUDA_OK(cudaEventRecord(c->ev_pass[fi][0], c->ce_stream[0]));
+    for (int j = 0; j < P; ++j) {
+      const int q = (me + 1 + j) % P;  // staggered: no two ranks start on the same destination
+      float2 *dst = ((two && fi == 1) ? c->recv2_peers[q] : c->peers.C[q]) + (size_t)me * chunk;
+      GH_CUDA_OK(cudaMemcpyAsync(dst, fields[fi] + (size_t)q * chunk, chunk * sizeof(float2), cudaMemcpyDefault,
+                                 c->ce_stream[j % GH_N_COPY_STREAMS]));
+    }
+    for (int k = 0; k < GH_N_COPY_STREAMS; ++k) GH_CUDA_OK(cudaEventRecord(c->ev_sent[fi][k], c->ce_stream[k]));
+    if (c->time_fft_passes) {
+      // the last copy stream to finish closes the interval: chain them on stream 0
+      for (int k = 1; k < GH_N_COPY_STREAMS; ++k) GH_CUDA_OK(cudaStreamWaitEvent(c->ce_stream[0], c->ev_sent[fi][k], 0));
+      GH_CUDA_OK(cudaEventRecord(c->ev_pass[fi][1], c->ce_stream[0]));
+    }
+    return 0;
+  };
+  auto landed = [&](int fi) -> int {
+    for (int k = 0; k < GH_N_COPY_STREAMS; ++k) GH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_sent[fi][k], 0));
+    return gh_stream_barrier(c);
+  };
+  // every rank is past its previous use of the receive buffers (last realisation's y passes, velocity, maps)
+  if (gh_stream_barrier(c)) return 1;
+  GH_CUDA_OK(cudaEventRecord(c->ev_free[0], c->stream));
+  if (two) GH_CUDA_OK(cudaEventRecord(c->ev_free[1], c->stream));
+  if (fft_z_pass<N>(c, c->gridA, false)) return 1;
+  GH_CUDA_OK(cudaEventRecord(c->ev_z[0], c->stream));
+  if (ship(0)) return 1;
+  if (fft_z_pass<N>(c, c->gridB, false)) return 1;
+  GH_CUDA_OK(cudaEventRecord(c->ev_z[1], c->stream));
+  if (two && ship(1)) return 1;
+  if (landed(0)) return 1;
+  if (two) {
+    if (fft_yx_passes<N>(c, c->gridA, c->gridC)) return 1;
+    if (landed(1)) return 1;
+    return fft_yx_passes<N>(c, c->gridB, c->recv2);
+  }
+  // one receive buffer: the y pass of A alone first (it is what reads C), then C is free on every rank
+  if (fft_yx_passes<N>(c, c->gridA, c->gridC)) return 1;
+  if (gh_stream_barrier(c)) return 1;
+  GH_CUDA_OK(cudaEventRecord(c->ev_free[1], c->stream));
+  if (ship(1)) return 1;
+  if (landed(1)) return 1;
+  return fft_yx_passes<N>(c, c->gridB, c->gridC);
+}
+
 }  // namespace
 
 int gh_fft_supported(int n)
 {
   return n == 32 || n == 64 || n == 128 || n == 256 || n == 512 || n == 1024 || n == 2048 || n == 4096;
+}
+
+int gh_launch_fft_both_fields(gh_cuda_ctx *c)
+{
+  if (c->d.nranks > 1 && c->have_peers && c->ce_transpose) {
+    switch (c->d.n) {
+      case 32: return fft_both_fields_ce<32>(c);
+      case 64: return fft_both_fields_ce<64>(c);
+      case 128: return fft_both_fields_ce<128>(c);
+      case 256: return fft_both_fields_ce<256>(c);
+      case 512: return fft_both_fields_ce<512>(c);
+      case 1024: return fft_both_fields_ce<1024>(c);
+      case 2048: return fft_both_fields_ce<2048>(c);
+      case 4096: return fft_both_fields_ce<4096>(c);
+      default: break;
+    }
+  }
+  if (gh_launch_fft_field(c, c->gridA)) return 1;  // src/fourier.c:391
+  return gh_launch_fft_field(c, c->gridB);         // src/fourier.c:392
 }
 
 int gh_launch_fft_field(gh_cuda_ctx *c, float2 *field)

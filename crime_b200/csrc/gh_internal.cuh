@@ -57,6 +57,7 @@ struct GhDev {
 
 #define GH_MAX_RANKS 16
 #define GH_MAX_CHUNKS 64
+#define GH_N_COPY_STREAMS 4
 
 // Peer views of the slab buffers of every rank (CUDA IPC mappings; entry [rank] is the local buffer).
 // Kernels use them to read or write other GPUs' memory over NVLink directly.
@@ -117,6 +118,13 @@ struct gh_cuda_ctx {
   int n_sm;
   int fft_stats_blocks;    // >0: the density FFT left that many per-CTA (sum, sumsq) partials in d_partials
   size_t fft_batch_bytes;  // plane batch of the fused y/x FFT passes (kept L2-resident)
+  // transposes on the copy engines, pipelined against the other field's passes (several ranks; gh_fft.cu)
+  bool ce_transpose;       // GH_FUSED_TRANSPOSE=1 restores the transpose fused into the z pass
+  cudaStream_t ce_stream[GH_N_COPY_STREAMS];
+  cudaEvent_t ev_z[2], ev_free[2], ev_sent[2][GH_N_COPY_STREAMS];
+  float2 *recv2;           // second receive buffer (the idle map stack, or an extra slab), nullptr: none
+  float2 *recv2_peers[GH_MAX_RANKS];
+  bool recv2_owned;        // recv2 is an allocation of its own
   bool fft_tma;            // strided FFT passes fetch their tiles with the TMA unit (GH_FFT_NO_TMA=1 turns it off)
   CUtensorMap fft_map[6];  // z pass of A, of B; y pass of A, of B: even rows; odd rows (wider box, see gh_fft.cu)
   bool fft_map_ok[4];
@@ -155,6 +163,7 @@ void gh_set_error(const char *fmt, ...);
 // stage launchers (each enqueues on ctx->stream and returns 0 / non-zero)
 int gh_launch_kgen(gh_cuda_ctx *c);
 int gh_launch_fft_field(gh_cuda_ctx *c, float2 *field);  // full c2r of one field incl. transpose + normalisation
+int gh_launch_fft_both_fields(gh_cuda_ctx *c);           // density then potential; pipelined transposes on several ranks
 int gh_fft_supported(int n);
 int gh_launch_radial_velocity(gh_cuda_ctx *c);
 int gh_launch_sigma(gh_cuda_ctx *c);  // leaves (sum, sumsq) in c->d_partials[0..1]

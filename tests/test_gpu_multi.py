@@ -16,12 +16,16 @@ def _ngpu():
 
 # bounds: GH_MAP_BOUNDS, forced plane ranges for the map accumulation (None = the cost model's; "off" = own slabs;
 # "nccl" = the cost model's ranges with GH_NO_SPARSE_REDUCE=1: ncclReduceScatter instead of the default sparse map reduction
-# over peer memory).
+# over peer memory; "fused" / "onebuf" / "ownbuf": the other routes of the FFT transposes -- fused into the z pass as
+# peer stores, copy engines with a single receive buffer, copy engines with a second buffer allocated for the purpose
+# instead of the idle map stack).
 # The forced cases make rank 0 pull planes from above, rank 1 from below, in more than one staging chunk, and
 # leave one rank without any of its own planes.
 @pytest.mark.parametrize("world,n_grid,n_side,bounds", [(2, 64, 32, None), (2, 64, 32, "57"), (2, 64, 32, "9"), (2, 64, 32, "off"),
                                                         (4, 128, 64, None), (4, 128, 64, "70,75,80"), (8, 128, 64, None),
-                                                        (2, 64, 32, "nccl"), (4, 128, 64, "nccl"), (8, 128, 64, "nccl")])
+                                                        (2, 64, 32, "nccl"), (4, 128, 64, "nccl"), (8, 128, 64, "nccl"),
+                                                        (2, 64, 32, "fused"), (2, 64, 32, "onebuf"), (2, 64, 32, "ownbuf"), (4, 128, 64, "onebuf"),
+                                                        (8, 128, 64, "fused"), (8, 128, 64, "ownbuf")])
 def test_slab_decomposition_matches_single_gpu(world, n_grid, n_side, bounds):
     import os
     if _ngpu() < world:
@@ -31,6 +35,8 @@ def test_slab_decomposition_matches_single_gpu(world, n_grid, n_side, bounds):
         env["GH_NO_REBALANCE"] = "1"
     elif bounds == "nccl":  # the NCCL collective instead of the sparse map reduction over peer memory
         env["GH_NO_SPARSE_REDUCE"] = "1"
+    elif bounds in ("fused", "onebuf", "ownbuf"):
+        env[{"fused": "GH_FUSED_TRANSPOSE", "onebuf": "GH_ONE_RECV_BUFFER", "ownbuf": "GH_OWN_RECV_BUFFER"}[bounds]] = "1"
     elif bounds:
         env["GH_MAP_BOUNDS"] = bounds
     _run_worker(world, n_grid, n_side, "full", env, f"{world}gpu_{n_grid}_{bounds or 'model'}")
