@@ -484,8 +484,24 @@ static int exchange_ipc(gh_cuda_ctx *c, void *mine_ptr, void **peers_out, bool *
 static int setup_ce_transpose(gh_cuda_ctx *c)
 {
   const GhDev &d = c->d;
-  c->ce_transpose = getenv("GH_FUSED_TRANSPOSE") == nullptr;
+  const char *mode = getenv("GH_TRANSPOSE");  // "ce" (default) | "nccl" | "fused"
+  c->ce_transpose = getenv("GH_FUSED_TRANSPOSE") == nullptr && !(mode && !strcmp(mode, "fused"));
   if (!c->ce_transpose) return 0;
+  if (mode && !strcmp(mode, "nccl")) {
+    // a second communicator for the transposes: its id travels through the first one
+    ncclUniqueId id2;
+    if (d.rank == 0) GH_NCCL_OK(ncclGetUniqueId(&id2));
+    char *d_id = nullptr;
+    GH_CUDA_OK(cudaMalloc(&d_id, sizeof(id2)));
+    GH_CUDA_OK(cudaMemcpyAsync(d_id, &id2, sizeof(id2), cudaMemcpyHostToDevice, c->stream));
+    GH_NCCL_OK(ncclBroadcast(d_id, d_id, sizeof(id2), ncclChar, 0, c->comm, c->stream));
+    GH_CUDA_OK(cudaMemcpyAsync(&id2, d_id, sizeof(id2), cudaMemcpyDeviceToHost, c->stream));
+    GH_CUDA_OK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_id);
+    GH_NCCL_OK(ncclCommInitRank(&c->comm2, d.nranks, id2, d.rank));
+    c->have_comm2 = true;
+    c->nccl_transpose = true;
+  }
   for (int k = 0; k < GH_N_COPY_STREAMS; ++k) GH_CUDA_OK(cudaStreamCreateWithFlags(&c->ce_stream[k], cudaStreamNonBlocking));
   for (int f = 0; f < 2; ++f) {
     GH_CUDA_OK(cudaEventCreateWithFlags(&c->ev_z[f], cudaEventDisableTiming));
@@ -549,6 +565,7 @@ extern "C" int gh_cuda_destroy(gh_cuda_ctx *c)
     if (q != c->d.rank && c->map_peers[q]) cudaIpcCloseMemHandle(c->map_peers[q]);
   cudaFree(c->d_ext);
   cudaFree(c->d_barrier);
+  if (c->have_comm2) ncclCommDestroy(c->comm2);
   if (c->have_comm) ncclCommDestroy(c->comm);
   cudaFree(c->gridA); cudaFree(c->gridB); cudaFree(c->gridC);
   cudaFree(c->halo_lo); cudaFree(c->halo_hi);

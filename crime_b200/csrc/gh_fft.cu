@@ -696,6 +696,23 @@ int fft_both_fields_ce(gh_cuda_ctx *c)
   float2 *fields[2] = {c->gridA, c->gridB};
   const bool two = c->recv2 != nullptr;
   auto ship = [&](int fi) -> int {
+    if (c->nccl_transpose) {
+      // two-sided: a rank's buffer is written only once it has posted the receives, so no barrier is involved
+      cudaStream_t s2 = c->ce_stream[0];
+      GH_CUDA_OK(cudaStreamWaitEvent(s2, c->ev_z[fi], 0));
+      GH_CUDA_OK(cudaStreamWaitEvent(s2, c->ev_free[fi], 0));
+      if (c->time_fft_passes) GH_CUDA_OK(cudaEventRecord(c->ev_pass[fi][0], s2));
+      float2 *recv = (two && fi == 1) ? c->recv2 : c->gridC;
+      GH_NCCL_OK(ncclGroupStart());
+      for (int q = 0; q < P; ++q) {
+        GH_NCCL_OK(ncclSend(fields[fi] + (size_t)q * chunk, chunk * 2, ncclFloat, q, c->comm2, s2));
+        GH_NCCL_OK(ncclRecv(recv + (size_t)q * chunk, chunk * 2, ncclFloat, q, c->comm2, s2));
+      }
+      GH_NCCL_OK(ncclGroupEnd());
+      for (int k = 0; k < GH_N_COPY_STREAMS; ++k) GH_CUDA_OK(cudaEventRecord(c->ev_sent[fi][k], s2));
+      if (c->time_fft_passes) GH_CUDA_OK(cudaEventRecord(c->ev_pass[fi][1], s2));
+      return 0;
+    }
     // copy streams start after the z pass of this field (ev_z[fi]) and after the barrier that freed the destination
     for (int k = 0; k < GH_N_COPY_STREAMS; ++k) {
       GH_CUDA_OK(cudaStreamWaitEvent(c->ce_stream[k], c->ev_z[fi], 0));
@@ -718,10 +735,10 @@ int fft_both_fields_ce(gh_cuda_ctx *c)
   };
   auto landed = [&](int fi) -> int {
     for (int k = 0; k < GH_N_COPY_STREAMS; ++k) GH_CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_sent[fi][k], 0));
-    return gh_stream_barrier(c);
+    return c->nccl_transpose ? 0 : gh_stream_barrier(c);
   };
   // every rank is past its previous use of the receive buffers (last realisation's y passes, velocity, maps)
-  if (gh_stream_barrier(c)) return 1;
+  if (!c->nccl_transpose && gh_stream_barrier(c)) return 1;
   GH_CUDA_OK(cudaEventRecord(c->ev_free[0], c->stream));
   if (two) GH_CUDA_OK(cudaEventRecord(c->ev_free[1], c->stream));
   if (fft_z_pass<N>(c, c->gridA, false)) return 1;
@@ -738,7 +755,7 @@ int fft_both_fields_ce(gh_cuda_ctx *c)
   }
   // one receive buffer: the y pass of A alone first (it is what reads C), then C is free on every rank
   if (fft_yx_passes<N>(c, c->gridA, c->gridC)) return 1;
-  if (gh_stream_barrier(c)) return 1;
+  if (!c->nccl_transpose && gh_stream_barrier(c)) return 1;
   GH_CUDA_OK(cudaEventRecord(c->ev_free[1], c->stream));
   if (ship(1)) return 1;
   if (landed(1)) return 1;

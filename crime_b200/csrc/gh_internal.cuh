@@ -120,6 +120,9 @@ struct gh_cuda_ctx {
   size_t fft_batch_bytes;  // plane batch of the fused y/x FFT passes (kept L2-resident)
   // transposes on the copy engines, pipelined against the other field's passes (several ranks; gh_fft.cu)
   bool ce_transpose;       // GH_FUSED_TRANSPOSE=1 restores the transpose fused into the z pass
+  bool nccl_transpose;     // the pipelined transposes as ncclSend/ncclRecv groups on a second communicator (GH_TRANSPOSE=nccl)
+  ncclComm_t comm2;        // used by the transposes only, on ce_stream[0]: never in flight together with `comm`
+  bool have_comm2;
   cudaStream_t ce_stream[GH_N_COPY_STREAMS];
   cudaEvent_t ev_z[2], ev_free[2], ev_sent[2][GH_N_COPY_STREAMS];
   float2 *recv2;           // second receive buffer (the idle map stack, or an extra slab), nullptr: none
