@@ -462,9 +462,12 @@ def main():
         dist.all_gather(allt, tt)
         per_rank = [{k: round(float(v), 3) for k, v in zip(abi.STAGE_NAMES, a.tolist())} for a in allt]
     nvlink = None
+    transpose_route = ("fused into the z pass" if os.environ.get("GH_FUSED_TRANSPOSE") or os.environ.get("GH_TRANSPOSE") == "fused"
+                       else "nccl send/recv, second communicator" if os.environ.get("GH_TRANSPOSE") == "nccl" else "copy engines")
     if world > 1:
-        # the z passes carry the transposes; every rank pushes (P-1)/P of its slab of each field to its peers inside
-        # them.  Slowest rank's time, so the figure is the all-to-all's, not one link's.
+        # the transposition phase of each field: every rank ships (P-1)/P of its slab to its peers -- copy-engine peer
+        # copies by default, the fused z pass with GH_FUSED_TRANSPOSE=1.  Slowest rank's time, so the figure is the
+        # all-to-all's, not one link's.
         zt = torch.tensor(list(z_pass), device=dev, dtype=torch.float64)
         dist.all_reduce(zt, op=dist.ReduceOp.MAX)
         z_ms = [float(v) for v in zt.tolist()]
@@ -473,9 +476,12 @@ def main():
             ach = 2 * sent / (sum(z_ms) * 1e-3) / 1e9
             nvlink = {"achieved": ach, "peak": 900.0, "unit": "GB/s per GPU per direction", "frac": ach / 900.0,
                       "z_pass_ms": z_ms, "bytes_sent_per_rank_per_field": sent,
-                      "what": "transpose fused into the FFT z pass (peer stores over NVLink while the pass computes), incl. the "
-                              "barrier that closes it, last e2e step; the pass also reads and transforms the slab, so this is a "
-                              "lower bound on the link rate; peak = NVLink 5 nominal"}
+                      "route": transpose_route,
+                      "what": ("copy-engine peer copies of the in-place z pass's output (one contiguous block per peer), first "
+                               "copy start to last copy end per field, overlapped with the other field's FFT passes; last e2e step; "
+                               "peak = NVLink 5 nominal" if transpose_route == "copy engines" else
+                               "transposition phase as timed by the library (fused: the z pass itself, which also reads and "
+                               "transforms the slab, so a lower bound on the link rate), last e2e step; peak = NVLink 5 nominal")}
         else:
             nvlink = {"achieved": None, "peak": 900.0, "unit": "GB/s per GPU per direction", "frac": None, "z_pass_ms": z_ms,
                       "what": "z-pass timers unavailable"}
