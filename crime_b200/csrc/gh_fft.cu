@@ -124,12 +124,20 @@ template <> struct Swz<2048, 4> { static constexpr int a = 0, b = 6, c = 31; };
 
 // tile layouts: LAY_PLAIN [position][line]; LAY_SWZ the same, XOR-swizzled; LAY_PAIR [position parity][position / 2][line],
 // which is how the TMA-fed y pass receives its tile (even and odd rows arrive as two boxes, see fft_strided_tma_kernel)
-enum { LAY_PLAIN = 0, LAY_SWZ = 1, LAY_PAIR = 2 };
+// LAY_PAD: [position][line] with a pitch of W + 1 float2 (odd pitch -> conflict-free along either index for one multiply-add
+// instead of the XOR swizzle's six integer operations per address).  Measured slower than the swizzle in the x pass
+// (512^3: FFT 1.65 vs 1.56 ms, 1024^3: 18.1 vs 16.3 ms; profiles/r2/ab_fft_rows_pad_*.log), so off: -DGH_FFT_ROWS_PAD=1 builds it
+enum { LAY_PLAIN = 0, LAY_SWZ = 1, LAY_PAIR = 2, LAY_PAD = 3 };
+#ifndef GH_FFT_ROWS_PAD
+#define GH_FFT_ROWS_PAD 0
+#endif
+template <int W> struct RowsLay { static constexpr int value = (W == 16 && GH_FFT_ROWS_PAD) ? LAY_PAD : LAY_SWZ; };
 
 template <int LEN, int W, int LAY = LAY_SWZ> __device__ __forceinline__ int phys(int pos, int w)
 {
   using S = Swz<LEN, W>;
   // odd rows: pitch W + 2, data from column 1 (their box starts one mode early to be 16-byte aligned)
+  if constexpr (LAY == LAY_PAD) return pos * (W + 1) + w;
   if constexpr (LAY == LAY_PAIR) return (pos & 1) ? (LEN / 2) * W + (pos >> 1) * (W + 2) + 1 + w : (pos >> 1) * W + w;
   const int a = pos * W + w;
   if constexpr (LAY == LAY_PLAIN) return a;
@@ -386,7 +394,7 @@ template <int H, int NTW, int W, int NT, int S>
 __device__ __forceinline__ void rows_passes(float2 *sm, const float2 *__restrict__ tw)
 {
   if constexpr (S < n_steps(H)) {
-    dif_pass_smem<H, NTW, W, NT, S, LAY_SWZ>(sm, tw);
+    dif_pass_smem<H, NTW, W, NT, S, RowsLay<W>::value>(sm, tw);
     __syncthreads();
     rows_passes<H, NTW, W, NT, S + 1>(sm, tw);
   }
@@ -426,8 +434,8 @@ __global__ void __launch_bounds__(NT) fft_c2r_rows_kernel(float2 *__restrict__ d
         zm = make_float2(e.x + t.y, t.x - e.y);
       }
     }
-    sm[phys<H, W>(k, row)] = zk;
-    sm[phys<H, W>(k == 0 ? H / 2 : H - k, row)] = zm;
+    sm[phys<H, W, RowsLay<W>::value>(k, row)] = zk;
+    sm[phys<H, W, RowsLay<W>::value>(k == 0 ? H / 2 : H - k, row)] = zm;
   }
   __syncthreads();
   rows_passes<H, N, W, NT, 0>(sm, tw);
@@ -437,7 +445,7 @@ __global__ void __launch_bounds__(NT) fft_c2r_rows_kernel(float2 *__restrict__ d
   for (int idx = tid; idx < W * H; idx += NT) {
     const int row = idx / H, m = idx % H;
     if (row0 + row < nrows) {
-      const float2 z = sm[phys<H, W>(freq_to_dif_pos<H>(m), row)];
+      const float2 z = sm[phys<H, W, RowsLay<W>::value>(freq_to_dif_pos<H>(m), row)];
       const float2 v = make_float2(z.x * norm, z.y * norm);
       data[(row0 + row) * ROW_STRIDE + m] = v;
       if (STATS) {
@@ -548,7 +556,7 @@ int launch_rows(gh_cuda_ctx *c, float2 *data, long long nrows, float norm, long 
 {
   using Cfg = FftCfg<N>;
   auto kern = fft_c2r_rows_kernel<N, Cfg::WR, Cfg::NT_R, STATS>;
-  const size_t smem = (size_t)Cfg::WR * (N / 2) * sizeof(float2);
+  const size_t smem = (size_t)(RowsLay<Cfg::WR>::value == LAY_PAD ? Cfg::WR + 1 : Cfg::WR) * (N / 2) * sizeof(float2);
   GH_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long blocks = (nrows + Cfg::WR - 1) / Cfg::WR;
   kern<<<(unsigned)blocks, Cfg::NT_R, smem, c->stream>>>(data, c->twiddle, nrows, norm, c->d_partials + 2 * first_block);

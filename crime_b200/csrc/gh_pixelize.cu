@@ -425,6 +425,7 @@ __global__ void __launch_bounds__(128, GH_ACC_MIN_BLOCKS) accumulate_kernel(cons
   const unsigned valid = active ? (nzv == 2 ? 0xFFu : 0x0Fu) : 0u;
   AuditCounts ac = {0, 0, 0, 0};
   float dz_min = 3.0e38f, dz_max = -3.0e38f;
+  float2 ms[4];  // masses of the block's cells, two per (plane, row)
 #pragma unroll
   for (int pz = 0; pz < 2; ++pz) {
 #pragma unroll
@@ -438,9 +439,7 @@ __global__ void __launch_bounds__(128, GH_ACC_MIN_BLOCKS) accumulate_kernel(cons
         dz_max = fmaxf(dz_max, fmaxf(z.x, z.y));
       }
       const int c = pz * 4 + py * 2;
-      // src/pixelize.c:203: float / int is a float division in C
-      s_w[c][tid] = __fdiv_rn(m.x, (float)GH_CUDA_N_SUBPART);
-      s_w[c + 1][tid] = __fdiv_rn(m.y, (float)GH_CUDA_N_SUBPART);
+      ms[pz * 2 + py] = m;
       s_dz[c][tid] = z.x;
       s_dz[c + 1][tid] = z.y;
     }
@@ -471,6 +470,13 @@ __global__ void __launch_bounds__(128, GH_ACC_MIN_BLOCKS) accumulate_kernel(cons
       }
     }
     if (!culled) {
+      // a tenth of each cell's mass (src/pixelize.c:203: float / int is a float division in C); only blocks that
+      // survive the cull pay for the eight divisions
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        s_w[2 * k][tid] = __fdiv_rn(ms[k].x, (float)GH_CUDA_N_SUBPART);
+        s_w[2 * k + 1][tid] = __fdiv_rn(ms[k].y, (float)GH_CUDA_N_SUBPART);
+      }
       const float dz_mid = 0.5f * (dz_min + dz_max);
       const GroupShells gs = group_shells(f, zs_lo, zs_hi, dz_mid);
       GhGroupExp g;
