@@ -463,7 +463,8 @@ def main():
         per_rank = [{k: round(float(v), 3) for k, v in zip(abi.STAGE_NAMES, a.tolist())} for a in allt]
     nvlink = None
     transpose_route = ("fused into the z pass" if os.environ.get("GH_FUSED_TRANSPOSE") or os.environ.get("GH_TRANSPOSE") == "fused"
-                       else "nccl send/recv, second communicator" if os.environ.get("GH_TRANSPOSE") == "nccl" else "copy engines")
+                       else "nccl send/recv, second communicator" if os.environ.get("GH_TRANSPOSE") == "nccl"
+                       else "store kernel over peer memory" if os.environ.get("GH_TRANSPOSE") == "push" else "copy engines")
     if world > 1:
         # the transposition phase of each field: every rank ships (P-1)/P of its slab to its peers -- copy-engine peer
         # copies by default, the fused z pass with GH_FUSED_TRANSPOSE=1.  Slowest rank's time, so the figure is the

@@ -502,7 +502,21 @@ static int setup_ce_transpose(gh_cuda_ctx *c)
     c->have_comm2 = true;
     c->nccl_transpose = true;
   }
-  for (int k = 0; k < GH_N_COPY_STREAMS; ++k) GH_CUDA_OK(cudaStreamCreateWithFlags(&c->ce_stream[k], cudaStreamNonBlocking));
+  {
+    // high priority: the transposes' CTAs (push kernel, NCCL) are scheduled ahead of the queued FFT CTAs
+    int lo = 0, hi = 0;
+    GH_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    for (int k = 0; k < GH_N_COPY_STREAMS; ++k) GH_CUDA_OK(cudaStreamCreateWithPriority(&c->ce_stream[k], cudaStreamNonBlocking, hi));
+  }
+  // One stream: the copies to the peers run one after the other in the staggered order, so at any moment the GPUs form a
+  // perfect matching and every link carries one full-rate copy.  Spreading them over several streams (concurrent copies to
+  // several peers) was measured to cut the rate to a third on 4 and 8 GPUs (4 GPUs, 1024^3: 685 GB/s with one stream, 370
+  // with two, 268 with four; profiles/r2/bench_4gpu_ce_streams_*.json)
+  c->ce_streams_used = getenv("GH_CE_STREAMS") ? atoi(getenv("GH_CE_STREAMS")) : 1;
+  if (c->ce_streams_used < 1 || c->ce_streams_used > GH_N_COPY_STREAMS) c->ce_streams_used = 1;
+  c->push_transpose = mode && !strcmp(mode, "push");
+  c->push_ctas = getenv("GH_PUSH_CTAS") ? atoi(getenv("GH_PUSH_CTAS")) : 64;
+  if (c->push_ctas < 1) c->push_ctas = 1;
   for (int f = 0; f < 2; ++f) {
     GH_CUDA_OK(cudaEventCreateWithFlags(&c->ev_z[f], cudaEventDisableTiming));
     GH_CUDA_OK(cudaEventCreateWithFlags(&c->ev_free[f], cudaEventDisableTiming));

@@ -686,6 +686,30 @@ int fft_field(gh_cuda_ctx *c, float2 *field)
   return fft_yx_passes<N, WSEL, NTSEL>(c, field, ysrc);
 }
 
+// The all-to-all as a kernel: a few persistent CTAs push this rank's blocks into the peers' receive buffers with 16-byte
+// loads and stores (NVLink writes are posted, so a store stream hides the link latency), on a high-priority stream next
+// to the FFT kernels of the other field.  Used instead of the copy engines with GH_TRANSPOSE=push: eight GPUs exchanging
+// at once brought the copy engines down to a third of the link rate.
+struct PushDst {
+  uint4 *p[GH_MAX_RANKS];
+};
+
+__global__ void __launch_bounds__(256) transpose_push_kernel(const uint4 *__restrict__ src, PushDst dst, long long chunk16, int me, int P)
+{
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (int j = 0; j < P; ++j) {
+    const int q = (me + 1 + j) % P;  // staggered: at any moment every rank writes to a different peer
+    const uint4 *s = src + (long long)q * chunk16;
+    uint4 *d = dst.p[q] + (long long)me * chunk16;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < chunk16; i += 4 * stride) {
+      const uint4 a = __ldcs(s + i), b = __ldcs(s + i + stride), c = __ldcs(s + i + 2 * stride), e = __ldcs(s + i + 3 * stride);
+      __stcs(d + i, a); __stcs(d + i + stride, b); __stcs(d + i + 2 * stride, c); __stcs(d + i + 3 * stride, e);
+    }
+    for (; i < chunk16; i += stride) __stcs(d + i, __ldcs(s + i));
+  }
+}
+
 // Both fields on several ranks with the transposes on the copy engines, pipelined against the compute passes:
 //   compute stream : barrier | z(A) | z(B)            | wait A, barrier | y(A) x(A) | wait B, barrier | y(B) x(B)
 //   copy streams   :         |      | A -> peers' C   | B -> peers' D   (NVLink, 1 large contiguous block per peer)
@@ -721,6 +745,20 @@ int fft_both_fields_ce(gh_cuda_ctx *c)
       if (c->time_fft_passes) GH_CUDA_OK(cudaEventRecord(c->ev_pass[fi][1], s2));
       return 0;
     }
+    if (c->push_transpose) {
+      cudaStream_t s2 = c->ce_stream[0];
+      GH_CUDA_OK(cudaStreamWaitEvent(s2, c->ev_z[fi], 0));
+      GH_CUDA_OK(cudaStreamWaitEvent(s2, c->ev_free[fi], 0));
+      if (c->time_fft_passes) GH_CUDA_OK(cudaEventRecord(c->ev_pass[fi][0], s2));
+      PushDst pd;
+      for (int q = 0; q < GH_MAX_RANKS; ++q)
+        pd.p[q] = q < P ? reinterpret_cast<uint4 *>((two && fi == 1) ? c->recv2_peers[q] : c->peers.C[q]) : nullptr;
+      transpose_push_kernel<<<c->push_ctas, 256, 0, s2>>>(reinterpret_cast<const uint4 *>(fields[fi]), pd, (long long)(chunk / 2), me, P);
+      GH_LAUNCH_CHECK(c);
+      for (int k = 0; k < GH_N_COPY_STREAMS; ++k) GH_CUDA_OK(cudaEventRecord(c->ev_sent[fi][k], s2));
+      if (c->time_fft_passes) GH_CUDA_OK(cudaEventRecord(c->ev_pass[fi][1], s2));
+      return 0;
+    }
     // copy streams start after the z pass of this field (ev_z[fi]) and after the barrier that freed the destination
     for (int k = 0; k < GH_N_COPY_STREAMS; ++k) {
       GH_CUDA_OK(cudaStreamWaitEvent(c->ce_stream[k], c->ev_z[fi], 0));
@@ -731,7 +769,7 @@ int fft_both_fields_ce(gh_cuda_ctx *c)
       const int q = (me + 1 + j) % P;  // staggered: no two ranks start on the same destination
       float2 *dst = ((two && fi == 1) ? c->recv2_peers[q] : c->peers.C[q]) + (size_t)me * chunk;
       GH_CUDA_OK(cudaMemcpyAsync(dst, fields[fi] + (size_t)q * chunk, chunk * sizeof(float2), cudaMemcpyDefault,
-                                 c->ce_stream[j % GH_N_COPY_STREAMS]));
+                                 c->ce_stream[j % c->ce_streams_used]));
     }
     for (int k = 0; k < GH_N_COPY_STREAMS; ++k) GH_CUDA_OK(cudaEventRecord(c->ev_sent[fi][k], c->ce_stream[k]));
     if (c->time_fft_passes) {

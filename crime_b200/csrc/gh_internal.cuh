@@ -121,9 +121,12 @@ struct gh_cuda_ctx {
   // transposes on the copy engines, pipelined against the other field's passes (several ranks; gh_fft.cu)
   bool ce_transpose;       // GH_FUSED_TRANSPOSE=1 restores the transpose fused into the z pass
   bool nccl_transpose;     // the pipelined transposes as ncclSend/ncclRecv groups on a second communicator (GH_TRANSPOSE=nccl)
+  bool push_transpose;     // the pipelined transposes as a store kernel on a high-priority stream (GH_TRANSPOSE=push)
+  int push_ctas;
   ncclComm_t comm2;        // used by the transposes only, on ce_stream[0]: never in flight together with `comm`
   bool have_comm2;
   cudaStream_t ce_stream[GH_N_COPY_STREAMS];
+  int ce_streams_used;     // GH_CE_STREAMS=1..4: how many of them the peer copies are spread over
   cudaEvent_t ev_z[2], ev_free[2], ev_sent[2][GH_N_COPY_STREAMS];
   float2 *recv2;           // second receive buffer (the idle map stack, or an extra slab), nullptr: none
   float2 *recv2_peers[GH_MAX_RANKS];

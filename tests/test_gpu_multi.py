@@ -26,7 +26,8 @@ def _ngpu():
                                                         (2, 64, 32, "nccl"), (4, 128, 64, "nccl"), (8, 128, 64, "nccl"),
                                                         (2, 64, 32, "fused"), (2, 64, 32, "onebuf"), (2, 64, 32, "ownbuf"), (4, 128, 64, "onebuf"),
                                                         (8, 128, 64, "fused"), (8, 128, 64, "ownbuf"),
-                                                        (2, 64, 32, "nccl2"), (2, 64, 32, "nccl2onebuf"), (8, 128, 64, "nccl2")])
+                                                        (2, 64, 32, "nccl2"), (2, 64, 32, "nccl2onebuf"), (8, 128, 64, "nccl2"),
+                                                        (2, 64, 32, "push"), (4, 128, 64, "push"), (8, 128, 64, "push")])
 def test_slab_decomposition_matches_single_gpu(world, n_grid, n_side, bounds):
     import os
     if _ngpu() < world:
@@ -36,10 +37,12 @@ def test_slab_decomposition_matches_single_gpu(world, n_grid, n_side, bounds):
         env["GH_NO_REBALANCE"] = "1"
     elif bounds == "nccl":  # the NCCL collective instead of the sparse map reduction over peer memory
         env["GH_NO_SPARSE_REDUCE"] = "1"
-    elif bounds.startswith("nccl2"):  # the pipelined transposes as NCCL send/recv groups on a second communicator
+    elif bounds and bounds.startswith("nccl2"):  # the pipelined transposes as NCCL send/recv groups on a second communicator
         env["GH_TRANSPOSE"] = "nccl"
         if bounds.endswith("onebuf"):
             env["GH_ONE_RECV_BUFFER"] = "1"
+    elif bounds == "push":  # the pipelined transposes as a store kernel over peer memory
+        env["GH_TRANSPOSE"] = "push"
     elif bounds in ("fused", "onebuf", "ownbuf"):
         env[{"fused": "GH_FUSED_TRANSPOSE", "onebuf": "GH_ONE_RECV_BUFFER", "ownbuf": "GH_OWN_RECV_BUFFER"}[bounds]] = "1"
     elif bounds:
