@@ -137,9 +137,12 @@ class GetHI:
         self.maps_HI = buf
         return buf
 
-    def run_async(self, slot: int = 0) -> np.ndarray:
-        """Enqueue a whole realisation without waiting; the maps land in pinned host buffer `slot` (0 or 1).
-        Call wait() before reading them."""
+    def run_async(self, slot: int | None = 0) -> np.ndarray | None:
+        """Enqueue a whole realisation without waiting; the maps land in pinned host buffer `slot` (0 or 1; None: they
+        stay on the device).  Call wait() before reading them."""
+        if slot is None:
+            self._check(self.lib.gh_cuda_run_async(self._ctx, None))
+            return None
         buf = self._host_maps(slot)
         self._check(self.lib.gh_cuda_run_async(self._ctx, _ptr(buf)))
         return buf
