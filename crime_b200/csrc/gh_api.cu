@@ -673,6 +673,7 @@ extern "C" int gh_cuda_create(const gh_cuda_params *p, int rank, int nranks, con
   }
   // gh_cuda_run*: radial velocity and get_HI in one pass (the multi-GPU parity check compares it with the staged calls)
   c->fuse_vel = getenv("GH_NO_FUSE_VEL") == nullptr;
+  c->defer_d2h = getenv("GH_NO_DEFER_D2H") == nullptr;  // measured: e2e loop 6.54 -> 6.27 ms per realisation at 512^3 (profiles/r2/e2e_probe*.log)
   // TMA-fed strided FFT passes: measured faster up to 512 (1.66 -> 1.56 ms both fields at 512^3), equal at 1024 (16.2 vs 16.4 ms),
   // slower at 2048 where the 64 KB tile is only 4 lines wide and the 32-byte store rows dominate (217 vs 168 ms on one GPU;
   // profiles/r2/): on by default for n_grid <= 512, GH_FFT_TMA=1 / GH_FFT_NO_TMA=1 force it on / off
@@ -987,7 +988,49 @@ extern "C" int gh_cuda_accumulate_maps(gh_cuda_ctx *c)
 }
 
 // accumulate -> (reduce-scatter) -> scale -> device->host copy on the copy stream; no host synchronisation
-static int enqueue_maps(gh_cuda_ctx *c, float *maps_host)
+// device -> host copy of a finished result on the copy stream, in chunks of whole shells (>= 32 MiB, at most
+// GH_MAX_CHUNKS of them), an event behind each, so that a consumer (the FITS writer) can start on the first shells
+// while the rest is on the wire.  The caller has made the copy stream wait for the result.
+static int issue_map_copy(gh_cuda_ctx *c, float *maps_host, const float *result, int n_here, int cur)
+{
+  const GhDev &d = c->d;
+  GH_CUDA_OK(cudaEventRecord(c->ev[2 * GH_T_D2H], c->copy_stream));
+  const size_t shell_bytes = (size_t)d.npix * sizeof(float);
+  int per = (int)((((size_t)32 << 20) + shell_bytes - 1) / shell_bytes);
+  if (per * GH_MAX_CHUNKS < n_here) per = (n_here + GH_MAX_CHUNKS - 1) / GH_MAX_CHUNKS;
+  c->chunk_shells = per;
+  c->n_chunks = 0;
+  for (int s = 0; s < n_here; s += per) {
+    const int ns = s + per < n_here ? per : n_here - s;
+    GH_CUDA_OK(cudaMemcpyAsync(maps_host + (size_t)s * d.npix, result + (size_t)s * d.npix, (size_t)ns * shell_bytes,
+                               cudaMemcpyDeviceToHost, c->copy_stream));
+    if (!c->ev_chunk[c->n_chunks]) GH_CUDA_OK(cudaEventCreateWithFlags(&c->ev_chunk[c->n_chunks], cudaEventDisableTiming));
+    GH_CUDA_OK(cudaEventRecord(c->ev_chunk[c->n_chunks], c->copy_stream));
+    c->n_chunks++;
+  }
+  GH_CUDA_OK(cudaEventRecord(c->ev[2 * GH_T_D2H + 1], c->copy_stream));
+  c->ev_used[GH_T_D2H] = true;
+  GH_CUDA_OK(cudaEventRecord(c->ev_copied[cur], c->copy_stream));
+  c->copy_pending[cur] = true;
+  c->copy_enqueued[cur] = true;
+  return 0;
+}
+
+// a download postponed by gh_cuda_run_async: enqueue it now, behind `after` on the compute stream if given
+static int flush_deferred_copy(gh_cuda_ctx *c, bool at_accumulate)
+{
+  if (!c->deferred_pending) return 0;
+  c->deferred_pending = false;
+  if (at_accumulate) {
+    if (!c->ev_acc) GH_CUDA_OK(cudaEventCreateWithFlags(&c->ev_acc, cudaEventDisableTiming));
+    GH_CUDA_OK(cudaEventRecord(c->ev_acc, c->stream));
+    GH_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_acc, 0));
+  }
+  GH_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_ready[c->deferred_cur], 0));
+  return issue_map_copy(c, c->deferred_host, c->deferred_result, c->deferred_n, c->deferred_cur);
+}
+
+static int enqueue_maps(gh_cuda_ctx *c, float *maps_host, bool defer_copy = false)
 {
   const GhDev &d = c->d;
   int n_here = 0, s0 = 0;
@@ -1001,12 +1044,14 @@ static int enqueue_maps(gh_cuda_ctx *c, float *maps_host)
   if (d.nranks == 1) {
     StageTimer t(c, GH_T_MAPS);
     if (gh_cuda_zero_maps(c)) return 1;
+    if (flush_deferred_copy(c, true)) return 1;  // the previous realisation's download rides along with this accumulation
     if (accumulate_own_slab(c)) return 1;
     if (gh_launch_scale_maps(c, c->maps, 0, d.n_nu)) return 1;
   } else {
     {
       StageTimer t(c, GH_T_MAPS);
       if (gh_cuda_zero_maps(c)) return 1;
+      if (flush_deferred_copy(c, true)) return 1;
       if ((c->rebalance && d.nz_here >= 2) ? accumulate_rebalanced(c) : accumulate_own_slab(c)) return 1;
     }
     {
@@ -1036,26 +1081,20 @@ static int enqueue_maps(gh_cuda_ctx *c, float *maps_host)
   c->n_chunks = 0;
   if (maps_host && n_here > 0) {
     GH_CUDA_OK(cudaEventRecord(c->ev_done, c->stream));
-    GH_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_done, 0));
-    GH_CUDA_OK(cudaEventRecord(c->ev[2 * GH_T_D2H], c->copy_stream));
-    // the copy goes out in chunks of whole shells (>= 32 MiB, at most GH_MAX_CHUNKS of them), an event behind
-    // each, so that a consumer (the FITS writer) can start on the first shells while the rest is on the wire
-    const size_t shell_bytes = (size_t)d.npix * sizeof(float);
-    int per = (int)((((size_t)32 << 20) + shell_bytes - 1) / shell_bytes);
-    if (per * GH_MAX_CHUNKS < n_here) per = (n_here + GH_MAX_CHUNKS - 1) / GH_MAX_CHUNKS;
-    c->chunk_shells = per;
-    for (int s = 0; s < n_here; s += per) {
-      const int ns = s + per < n_here ? per : n_here - s;
-      GH_CUDA_OK(cudaMemcpyAsync(maps_host + (size_t)s * d.npix, result + (size_t)s * d.npix, (size_t)ns * shell_bytes,
-                                 cudaMemcpyDeviceToHost, c->copy_stream));
-      if (!c->ev_chunk[c->n_chunks]) GH_CUDA_OK(cudaEventCreateWithFlags(&c->ev_chunk[c->n_chunks], cudaEventDisableTiming));
-      GH_CUDA_OK(cudaEventRecord(c->ev_chunk[c->n_chunks], c->copy_stream));
-      c->n_chunks++;
+    if (defer_copy && c->out_buf[1]) {  // (needs the second result buffer: the next realisation must not touch this one)
+      // gh_cuda_run_async: the download starts when the NEXT realisation reaches its map accumulation (or at
+      // gh_cuda_wait): next to the memory-bound FFT passes it costs them ~0.4 ms at 512^3, next to the issue-bound
+      // accumulation much less
+      if (!c->ev_ready[cur]) GH_CUDA_OK(cudaEventCreateWithFlags(&c->ev_ready[cur], cudaEventDisableTiming));
+      GH_CUDA_OK(cudaEventRecord(c->ev_ready[cur], c->stream));
+      c->deferred_host = maps_host; c->deferred_result = result; c->deferred_n = n_here; c->deferred_cur = cur;
+      c->deferred_pending = true;
+      c->copy_pending[cur] = true;  // nobody may zero this buffer before its copy, which is not even enqueued yet
+      c->copy_enqueued[cur] = false;
+      return 0;
     }
-    GH_CUDA_OK(cudaEventRecord(c->ev[2 * GH_T_D2H + 1], c->copy_stream));
-    c->ev_used[GH_T_D2H] = true;
-    GH_CUDA_OK(cudaEventRecord(c->ev_copied[cur], c->copy_stream));
-    c->copy_pending[cur] = true;
+    GH_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, c->ev_done, 0));
+    if (issue_map_copy(c, maps_host, result, n_here, cur)) return 1;
   }
   return 0;
 }
@@ -1083,6 +1122,7 @@ extern "C" int gh_cuda_wait_shells(gh_cuda_ctx *c, int n_shells)
 extern "C" int gh_cuda_wait(gh_cuda_ctx *c, double *sigma2_out)
 {
   GH_CTX(c);
+  if (flush_deferred_copy(c, false)) return 1;
   GH_CUDA_OK(cudaStreamSynchronize(c->stream));
   for (int b = 0; b < 2; ++b) {
     if (c->copy_pending[b]) GH_CUDA_OK(cudaEventSynchronize(c->ev_copied[b]));
@@ -1123,7 +1163,7 @@ extern "C" int gh_cuda_run_async(gh_cuda_ctx *c, float *maps_host)
     if (enqueue_sigma(c)) return 1;
     if (gh_cuda_get_HI(c)) return 1;
   }
-  return enqueue_maps(c, maps_host);
+  return enqueue_maps(c, maps_host, c->defer_d2h);
 }
 
 extern "C" int gh_cuda_run(gh_cuda_ctx *c, double *sigma2_out, float *maps_host)

@@ -73,6 +73,13 @@ struct gh_cuda_ctx {
   cudaStream_t copy_stream;        // device->host copy of the finished maps, overlaps the next realisation
   cudaEvent_t ev_done, ev_copied[2];
   bool copy_pending[2], sigma_ready;
+  bool copy_enqueued[2];           // the pending copy of that buffer has been handed to the copy stream (see defer_d2h)
+  bool defer_d2h;                  // gh_cuda_run_async postpones a download to the next realisation's accumulation (default; GH_NO_DEFER_D2H=1 turns it off)
+  bool deferred_pending;
+  float *deferred_host;
+  const float *deferred_result;
+  int deferred_n, deferred_cur;
+  cudaEvent_t ev_ready[2], ev_acc;
   float *out_buf[2];               // what the device->host copy reads (maps on one rank, maps_recv on several), doubled when it fits
   int out_cur;
   char *h_stage[2];                // pinned staging of the tables + prefactors, used alternately
