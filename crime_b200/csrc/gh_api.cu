@@ -267,16 +267,7 @@ static int apply_params(gh_cuda_ctx *c, const gh_cuda_params *p, int rank, int n
     for (int i = 0; i < 3 * GH_CUDA_N_SUBPART; ++i) d.sub_off_f[i] = (float)d.sub_off[i];
     for (int i = 0; i < GH_CUDA_N_SUBPART; ++i) {
       const float ox = d.sub_off_f[i], oy = d.sub_off_f[GH_CUDA_N_SUBPART + i], oz = d.sub_off_f[2 * GH_CUDA_N_SUBPART + i];
-      float *m = d.sub_mono;
       d.sub_c[i] = make_float4(ox, oy, oz, ox * ox + oy * oy + oz * oz);
-      m[i] = ox * ox + oy * oy + oz * oz;
-      m[GH_CUDA_N_SUBPART + i] = ox * ox - oy * oy;
-      m[2 * GH_CUDA_N_SUBPART + i] = ox * oy;
-      m[3 * GH_CUDA_N_SUBPART + i] = ox * ox;
-      m[4 * GH_CUDA_N_SUBPART + i] = oy * oy;
-      m[5 * GH_CUDA_N_SUBPART + i] = oz * oz;
-      m[6 * GH_CUDA_N_SUBPART + i] = ox * oz;
-      m[7 * GH_CUDA_N_SUBPART + i] = oy * oz;
     }
   }
   {

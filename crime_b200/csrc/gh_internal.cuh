@@ -43,10 +43,7 @@ struct GhDev {
   double z_lo_cull, z_hi_cull; // redshift window outside of which no sub-particle can land in a shell
   double sub_off[3 * GH_CUDA_N_SUBPART];
   float sub_off_f[3 * GH_CUDA_N_SUBPART];
-  // monomials of the float offsets for the per-cell Taylor pixelisation (GH_ACC_TAYLOR): |o|^2, ox^2-oy^2, ox*oy,
-  // ox^2, oy^2, oz^2, ox*oz, oy*oz
-  float sub_mono[8 * GH_CUDA_N_SUBPART];
-  // (ox, oy, oz, |o|^2) of each float offset: one 16-byte uniform load per sub-particle in the unrolled Taylor loop
+  // (ox, oy, oz, |o|^2) of each float offset: one 16-byte constant load per sub-particle in the block-expansion loops
   float4 sub_c[GH_CUDA_N_SUBPART];
 };
 
