@@ -1,12 +1,15 @@
 // mk_T_maps on sm_100a (reference src/pixelize.c:150-262): every cell is split into 10 sub-particles at
 // fixed offsets, each is sent to (frequency shell, HEALPix RING pixel) and deposits a tenth of the cell's
-// HI mass.  Shell and pixel indices must equal the reference's bit for bit, so this translation unit is
-// built with -fmad=false and does the geometry in IEEE double (gh_index_math.cuh).
+// HI mass.  Shell and pixel indices must equal the reference's bit for bit: the exact arithmetic (IEEE double,
+// this translation unit is built with -fmad=false) lives in gh_index_math.cuh; two fp32 fast paths in front of
+// it -- the 2x2x2-block expansion of gh_group_math.cuh and, for the few cells it does not cover, a per-cell
+// path -- accept their own answer only when every decision is clear of its error bound, and hand the rest to
+// the exact path.
 //
-// The stage is bound by double-precision instruction and L2-atomic throughput, not by HBM (8 B/cell of
-// grid traffic against ~10 sub-particles x ~150 fp64 instructions): cells whose whole extent lies
-// outside the shells' redshift window are culled by a conservative radial bound first (about half of
-// the box for the shipped frequency table).
+// The stage is bound by instruction issue and L2-atomic throughput, not by HBM (8 B/cell of grid traffic
+// against ~60 instructions per sub-particle); blocks whose whole extent lies outside the shells' redshift
+// window are culled by a conservative radial bound first (about 44 % of the box for the shipped frequency
+// table).  DESIGN.md section 4 has the measurements.
 #include "gh_internal.cuh"
 #include "gh_index_math.cuh"
 #include "gh_group_math.cuh"
