@@ -607,7 +607,9 @@ extern "C" int gh_cuda_create(const gh_cuda_params *p, int rank, int nranks, con
   GH_REQUIRE(p && ctx_out, "gh_cuda_create: null argument");
   *ctx_out = nullptr;
   GH_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "gh_cuda_create: bad rank %d of %d", rank, nranks);
-  GH_REQUIRE(gh_fft_supported(p->n_grid), "n_grid=%d unsupported (powers of two 32..4096)", p->n_grid);
+  GH_REQUIRE(gh_fft_supported(p->n_grid), "n_grid=%d unsupported (even, 8..4096)", p->n_grid);
+  GH_REQUIRE(nranks == 1 || gh_fft_tuned(p->n_grid),
+             "n_grid=%d unsupported on %d ranks (several ranks need a power of two 32..4096; other even sizes run on one)", p->n_grid, nranks);
   GH_REQUIRE((nranks & (nranks - 1)) == 0 && p->n_grid % nranks == 0 && p->n_grid / nranks >= 2,
              "n_grid=%d cannot be split into %d slabs (need a power-of-two rank count, >=2 planes each)", p->n_grid, nranks);
   GH_REQUIRE(p->n_side >= 1 && p->n_nu >= 1 && p->n_nu <= 4096, "bad n_side=%ld / n_nu=%d", p->n_side, p->n_nu);

@@ -22,6 +22,7 @@
 // 8-byte accesses; the strided kernel's [position][line] tile is conflict-free as it is (lines are the fast
 // index in both global and shared memory), so it uses plain addressing.
 #include "gh_internal.cuh"
+#include "gh_fft_generic.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -808,9 +809,66 @@ int fft_both_fields_ce(gh_cuda_ctx *c)
   return fft_yx_passes<N>(c, c->gridB, c->gridC);
 }
 
+// ---- any other even n_grid: generic-length passes (gh_fft_generic.cuh) ----------------------------------------
+// The reference's FFTW takes any n_grid (src/fourier.c:85-99); the kernels above exist for powers of two.  Everything
+// else runs the same three in-place passes (z, y, x with the normalisation fused) through one runtime-length kernel pair:
+// a tile of W adjacent lines in shared memory, mixed-radix Stockham passes between two buffers, natural-order output.
+// One rank only (the transposes above are written for power-of-two slabs).
+__global__ void __launch_bounds__(256) fft_generic_strided_kernel(float2 *data, const float2 *__restrict__ tw, const __grid_constant__ GfftPlan plan,
+                                                                  int W, const __grid_constant__ GfftGeom g)
+{
+  extern __shared__ float2 sm[];
+  for (int phase = 0; phase < plan.nfact + 2; ++phase) {
+    gfft_strided_cta_phase(phase, sm, data, tw, plan, W, g, blockIdx.x, threadIdx.x, blockDim.x);
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) fft_generic_rows_kernel(float2 *data, const float2 *__restrict__ tw, const __grid_constant__ GfftPlan plan, int W,
+                                                               int pitch,
+                                                               long long nrows, int nh, float norm)
+{
+  extern __shared__ float2 sm[];
+  for (int phase = 0; phase < plan.nfact + 2; ++phase) {
+    gfft_rows_cta_phase(phase, sm, data, tw, plan, W, pitch, nrows, nh, norm, blockIdx.x, threadIdx.x, blockDim.x);
+    __syncthreads();
+  }
+}
+
+int fft_field_generic(gh_cuda_ctx *c, float2 *field)
+{
+  const GhDev &d = c->d;
+  if (d.nranks != 1) {
+    gh_set_error("n_grid=%d is not a power of two: the general-length FFT runs on one rank only", d.n);
+    return 1;
+  }
+  GfftLaunch L;
+  if (!gfft_make_launch(d.n, d.nz_here, &L)) {
+    gh_set_error("n_grid=%d: the general-length FFT needs an even n_grid whose lines fit in shared memory twice", d.n);
+    return 1;
+  }
+  GH_CUDA_OK(cudaFuncSetAttribute(fft_generic_strided_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem_s));
+  GH_CUDA_OK(cudaFuncSetAttribute(fft_generic_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem_r));
+  fft_generic_strided_kernel<<<(unsigned)L.blocks_z, 256, L.smem_s, c->stream>>>(field, c->twiddle, L.pn, L.W, L.gz);
+  GH_LAUNCH_CHECK(c);
+  fft_generic_strided_kernel<<<(unsigned)L.blocks_y, 256, L.smem_s, c->stream>>>(field, c->twiddle, L.pn, L.W, L.gy);
+  GH_LAUNCH_CHECK(c);
+  const double normd = pow(sqrt(2.0 * 3.14159265358979323846) / d.l_box, 3.0);  // src/fourier.c:403
+  fft_generic_rows_kernel<<<(unsigned)L.blocks_x, 256, L.smem_r, c->stream>>>(field, c->twiddle, L.ph, L.WR, L.pitch, L.nrows, d.nh, (float)normd);
+  GH_LAUNCH_CHECK(c);
+  return 0;
+}
+
 }  // namespace
 
 int gh_fft_supported(int n)
+{
+  // powers of two 32..4096 have tuned kernels; every other even n_grid takes the general-length passes
+  return n >= 8 && n <= 4096 && (n & 1) == 0;
+}
+
+// lengths with tuned kernels (and the only ones the multi-rank transposes are written for)
+int gh_fft_tuned(int n)
 {
   return n == 32 || n == 64 || n == 128 || n == 256 || n == 512 || n == 1024 || n == 2048 || n == 4096;
 }
@@ -845,8 +903,6 @@ int gh_launch_fft_field(gh_cuda_ctx *c, float2 *field)
     case 1024: return fft_field<1024>(c, field);
     case 2048: return fft_field<2048>(c, field);
     case 4096: return fft_field<4096>(c, field);
-    default:
-      gh_set_error("n_grid=%d is not supported by the sm_100a FFT (powers of two 32..4096)", c->d.n);
-      return 1;
+    default: return fft_field_generic(c, field);
   }
 }

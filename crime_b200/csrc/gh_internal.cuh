@@ -174,7 +174,8 @@ void gh_set_error(const char *fmt, ...);
 int gh_launch_kgen(gh_cuda_ctx *c);
 int gh_launch_fft_field(gh_cuda_ctx *c, float2 *field);  // full c2r of one field incl. transpose + normalisation
 int gh_launch_fft_both_fields(gh_cuda_ctx *c);           // density then potential; pipelined transposes on several ranks
-int gh_fft_supported(int n);
+int gh_fft_supported(int n);  // any even n_grid in 8..4096
+int gh_fft_tuned(int n);      // powers of two 32..4096: tuned kernels, any power-of-two rank count
 int gh_launch_radial_velocity(gh_cuda_ctx *c);
 int gh_launch_sigma(gh_cuda_ctx *c);  // leaves (sum, sumsq) in c->d_partials[0..1]
 int gh_launch_sigma_finish(gh_cuda_ctx *c);  // d_partials[4] = mean, [5] = measured sigma2_gauss

@@ -51,9 +51,12 @@ def test_create_fails_loudly_without_gpu_or_with_bad_params(tables_nu64):
     bad = abi.GhCudaParams()
     assert lib.gh_cuda_create(C.byref(bad), 0, 1, None, 0, C.byref(ctx)) != 0
     assert b"n_grid" in lib.gh_cuda_last_error()
-    p = params_from_tables(tables_nu64, n_grid=48, n_side=8)
+    p = params_from_tables(tables_nu64, n_grid=47, n_side=8)  # odd: the half-complex layout needs an even grid
     assert lib.gh_cuda_create(C.byref(p), 0, 1, None, 0, C.byref(ctx)) != 0
     assert b"unsupported" in lib.gh_cuda_last_error()
+    p = params_from_tables(tables_nu64, n_grid=48, n_side=8)  # general-length FFT: one rank only
+    assert lib.gh_cuda_create(C.byref(p), 0, 2, b"\0" * 128, 0, C.byref(ctx)) != 0
+    assert b"unsupported on 2 ranks" in lib.gh_cuda_last_error()
     p = params_from_tables(tables_nu64, n_grid=64, n_side=8)
     assert lib.gh_cuda_create(C.byref(p), 0, 3, None, 0, C.byref(ctx)) != 0  # 3 ranks: not a power of two
     if not torch.cuda.is_available():
