@@ -1,6 +1,7 @@
 /* TEST INFRASTRUCTURE ONLY -- stand-in for <fitsio.h> (cfitsio, unpinned).  Implements just enough of
  * the write path used by he_write_healpix_map (healpix_extra.c:132-164): an empty primary HDU plus one
- * BINTABLE extension with big-endian 1E columns in 2880-byte blocks.  Read entry points are link-only. */
+ * BINTABLE extension with big-endian 1E columns in 2880-byte blocks; and of the read path of he_read_healpix_map
+ * (healpix_extra.c:166-224): HDU walk, integer / string keys, rE / rD columns. */
 #ifndef SHIM_FITSIO_H
 #define SHIM_FITSIO_H
 typedef struct shim_fitsfile fitsfile;

@@ -386,9 +386,20 @@ def test_c_host_executable_end_to_end(tmp_path, oracle):
         ref = g.run().copy()
     lines = (tmp_path / "run_nuTable.dat").read_text().splitlines()
     assert len(lines) == 16 and lines[0].split()[0] == "1"
+    from oracle.binding import Reference
+    ref_reader = None
+    if Reference.available():  # the compiled reference's own he_read_healpix_map (src/healpix_extra.c:166-224), as JoinT would open the files
+        import ctypes as C
+        ref_reader = Reference().lib.he_read_healpix_map
+        ref_reader.argtypes = [C.c_char_p, C.POINTER(C.c_long), C.c_int]
+        ref_reader.restype = C.POINTER(C.c_float)
     for s in range(16):
         m, hdr = host.read_healpix_map(tmp_path / f"run_{s + 1:03d}.fits")
         assert int(hdr["NSIDE"]) == 32
+        if ref_reader is not None:
+            ns = C.c_long(-1)
+            ptr = ref_reader(str(tmp_path / f"run_{s + 1:03d}.fits").encode(), C.byref(ns), 0)
+            assert ns.value == 32 and np.array_equal(np.ctypeslib.as_array(ptr, shape=(12 * 32 * 32,)), m)
         nz = ref[s] != 0
         assert np.array_equal(m != 0, nz)
         if nz.any():
