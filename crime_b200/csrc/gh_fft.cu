@@ -809,28 +809,31 @@ int fft_both_fields_ce(gh_cuda_ctx *c)
   return fft_yx_passes<N>(c, c->gridB, c->gridC);
 }
 
-// ---- any other even n_grid: generic-length passes (gh_fft_generic.cuh) ----------------------------------------
+// ---- any other even n_grid: general-length passes (gh_fft_generic.cuh) ----------------------------------------
 // The reference's FFTW takes any n_grid (src/fourier.c:85-99); the kernels above exist for powers of two.  Everything
 // else runs the same three in-place passes (z, y, x with the normalisation fused) through one runtime-length kernel pair:
 // a tile of W adjacent lines in shared memory, mixed-radix Stockham passes between two buffers, natural-order output.
+// The CTA bodies live in gh_fft_generic.cuh as __host__ __device__ phase functions so that the CPU tests execute the very
+// same code (tests/test_fft_generic_cpu.py).  Measured on a B200 (both fields): 384^3 2.1 ms, 640^3 10.8 ms, 768^3 17.9 ms,
+// 1536^3 160 ms, i.e. 23-27 Gcells/s against 86 for the tuned 512^3 kernels (profiles/r2/generic_grid_quickcheck_*.log).
 // One rank only (the transposes above are written for power-of-two slabs).
 __global__ void __launch_bounds__(256) fft_generic_strided_kernel(float2 *data, const float2 *__restrict__ tw, const __grid_constant__ GfftPlan plan,
-                                                                  int W, const __grid_constant__ GfftGeom g)
+                                                                  int W, const __grid_constant__ GfftGeom g, int fast)
 {
   extern __shared__ float2 sm[];
   for (int phase = 0; phase < plan.nfact + 2; ++phase) {
-    gfft_strided_cta_phase(phase, sm, data, tw, plan, W, g, blockIdx.x, threadIdx.x, blockDim.x);
+    gfft_strided_cta_phase(phase, sm, data, tw, plan, W, g, fast, blockIdx.x, threadIdx.x, blockDim.x);
     __syncthreads();
   }
 }
 
 __global__ void __launch_bounds__(256) fft_generic_rows_kernel(float2 *data, const float2 *__restrict__ tw, const __grid_constant__ GfftPlan plan, int W,
                                                                int pitch,
-                                                               long long nrows, int nh, float norm)
+                                                               long long nrows, int nh, float norm, int fast)
 {
   extern __shared__ float2 sm[];
   for (int phase = 0; phase < plan.nfact + 2; ++phase) {
-    gfft_rows_cta_phase(phase, sm, data, tw, plan, W, pitch, nrows, nh, norm, blockIdx.x, threadIdx.x, blockDim.x);
+    gfft_rows_cta_phase(phase, sm, data, tw, plan, W, pitch, nrows, nh, norm, fast, blockIdx.x, threadIdx.x, blockDim.x);
     __syncthreads();
   }
 }
@@ -847,14 +850,18 @@ int fft_field_generic(gh_cuda_ctx *c, float2 *field)
     gh_set_error("n_grid=%d: the general-length FFT needs an even n_grid whose lines fit in shared memory twice", d.n);
     return 1;
   }
+  // one thread per butterfly for the radices 2, 3, 4, 5, 7, one per output element for any other prime; GH_FFT_GENERIC_SLOW=1:
+  // one per output element throughout, the first version (both validated on a B200 against the oracle; 3.2x apart:
+  // profiles/r2/generic_grid_*.log)
+  const int fast = getenv("GH_FFT_GENERIC_SLOW") == nullptr;
   GH_CUDA_OK(cudaFuncSetAttribute(fft_generic_strided_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem_s));
   GH_CUDA_OK(cudaFuncSetAttribute(fft_generic_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem_r));
-  fft_generic_strided_kernel<<<(unsigned)L.blocks_z, 256, L.smem_s, c->stream>>>(field, c->twiddle, L.pn, L.W, L.gz);
+  fft_generic_strided_kernel<<<(unsigned)L.blocks_z, 256, L.smem_s, c->stream>>>(field, c->twiddle, L.pn, L.W, L.gz, fast);
   GH_LAUNCH_CHECK(c);
-  fft_generic_strided_kernel<<<(unsigned)L.blocks_y, 256, L.smem_s, c->stream>>>(field, c->twiddle, L.pn, L.W, L.gy);
+  fft_generic_strided_kernel<<<(unsigned)L.blocks_y, 256, L.smem_s, c->stream>>>(field, c->twiddle, L.pn, L.W, L.gy, fast);
   GH_LAUNCH_CHECK(c);
   const double normd = pow(sqrt(2.0 * 3.14159265358979323846) / d.l_box, 3.0);  // src/fourier.c:403
-  fft_generic_rows_kernel<<<(unsigned)L.blocks_x, 256, L.smem_r, c->stream>>>(field, c->twiddle, L.ph, L.WR, L.pitch, L.nrows, d.nh, (float)normd);
+  fft_generic_rows_kernel<<<(unsigned)L.blocks_x, 256, L.smem_r, c->stream>>>(field, c->twiddle, L.ph, L.WR, L.pitch, L.nrows, d.nh, (float)normd, fast);
   GH_LAUNCH_CHECK(c);
   return 0;
 }

@@ -80,6 +80,82 @@ GFFT_HD void gfft_pass(const float2 *x, float2 *y, const float2 *tw, int tws, in
   }
 }
 
+// The same pass with one thread per butterfly instead of one per output element, for the radices worth a register array
+// (2, 3, 4, 5, 7): the R inputs are read once, the R outputs leave together.  Bit-for-bit the arithmetic of gfft_pass for
+// R = 3, 5, 7 (same products, same summation order); R = 2 and 4 use the exact +-1 / +-i butterflies instead of table
+// look-ups of those values.  fast = 0 in the launch geometry keeps every pass on gfft_pass.
+template <int R>
+GFFT_HD void gfft_pass_small(const float2 *x, float2 *y, const float2 *tw, int tws, int n, int W, int pitch, int n_cur, int s, int tid,
+                             int nthreads)
+{
+  const int m = n_cur / R;
+  const int step_r = (n / R) * tws;
+  const int in_stride = s * m * pitch, out_stride = s * pitch;
+  for (int item = tid; item < (n / R) * W; item += nthreads) {
+    const int w = item % W, b = item / W;  // butterfly b = q + s p
+    const int q = b % s, p = b / s;
+    const float2 *xi = x + b * pitch + w;
+    float2 a[R], o[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) a[j] = xi[j * in_stride];
+    if (R == 2) {
+      o[0] = make_float2(a[0].x + a[1].x, a[0].y + a[1].y);
+      o[1] = make_float2(a[0].x - a[1].x, a[0].y - a[1].y);
+    } else if (R == 4) {
+      const float2 e = make_float2(a[0].x + a[2].x, a[0].y + a[2].y), f = make_float2(a[0].x - a[2].x, a[0].y - a[2].y);
+      const float2 g = make_float2(a[1].x + a[3].x, a[1].y + a[3].y), d = make_float2(a[1].x - a[3].x, a[1].y - a[3].y);
+      o[0] = make_float2(e.x + g.x, e.y + g.y);
+      o[1] = make_float2(f.x - d.y, f.y + d.x);  // + i d
+      o[2] = make_float2(e.x - g.x, e.y - g.y);
+      o[3] = make_float2(f.x + d.y, f.y - d.x);  // - i d
+    } else {
+      float2 wr[R];  // exp(2 pi i j / R)
+#pragma unroll
+      for (int j = 1; j < R; ++j) wr[j] = tw[j * step_r];
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        float ax = a[0].x, ay = a[0].y;
+#pragma unroll
+        for (int j = 1; j < R; ++j) {
+          const float2 c = wr[(j * k) % R == 0 ? 1 : (j * k) % R];  // (j k) % R == 0 only for k == 0, handled below
+          if (k == 0) {
+            ax += a[j].x;
+            ay += a[j].y;
+          } else {
+            ax += a[j].x * c.x - a[j].y * c.y;
+            ay += a[j].x * c.y + a[j].y * c.x;
+          }
+        }
+        o[k] = make_float2(ax, ay);
+      }
+    }
+    float2 *yo = y + (q + s * R * p) * pitch + w;
+    yo[0] = o[0];
+    const int et = p * s * tws;  // exp(2 pi i p k / n_cur) = tw[k et], k p < n_cur
+#pragma unroll
+    for (int k = 1; k < R; ++k) {
+      const float2 c = tw[k * et];
+      yo[k * out_stride] = make_float2(o[k].x * c.x - o[k].y * c.y, o[k].x * c.y + o[k].y * c.x);
+    }
+  }
+}
+
+GFFT_HD void gfft_pass_any(int fast, const float2 *x, float2 *y, const float2 *tw, int tws, int n, int W, int pitch, int r, int n_cur,
+                           int s, int tid, int nthreads)
+{
+  if (fast) {
+    switch (r) {
+      case 2: gfft_pass_small<2>(x, y, tw, tws, n, W, pitch, n_cur, s, tid, nthreads); return;
+      case 3: gfft_pass_small<3>(x, y, tw, tws, n, W, pitch, n_cur, s, tid, nthreads); return;
+      case 4: gfft_pass_small<4>(x, y, tw, tws, n, W, pitch, n_cur, s, tid, nthreads); return;
+      case 5: gfft_pass_small<5>(x, y, tw, tws, n, W, pitch, n_cur, s, tid, nthreads); return;
+      case 7: gfft_pass_small<7>(x, y, tw, tws, n, W, pitch, n_cur, s, tid, nthreads); return;
+      default: break;
+    }
+  }
+  gfft_pass(x, y, tw, tws, n, W, pitch, r, n_cur, s, tid, nthreads);
+}
+
 // Strided axis: line w of the tile is src[w], element pos of a line sits pos * stride further on.
 GFFT_HD void gfft_load_strided(float2 *x, const float2 *src, long long stride, int n, int W, int nvalid, int tid, int nthreads)
 {
@@ -162,7 +238,7 @@ GFFT_HD void gfft_pass_state(const GfftPlan &plan, int f, int &n_cur, int &s)
 
 // strided axis (z: one flat group of n * nh columns; y: one group per z plane), W lines per CTA, pitch W
 GFFT_HD void gfft_strided_cta_phase(int phase, float2 *sm, float2 *data, const float2 *tw, const GfftPlan &plan, int W,
-                                    const GfftGeom &g, long long block, int tid, int nthreads)
+                                    const GfftGeom &g, int fast, long long block, int tid, int nthreads)
 {
   const int n = plan.n;
   float2 *const b0 = sm, *const b1 = sm + (size_t)n * W;  // buffer i holds the tile after pass i (i & 1)
@@ -175,7 +251,7 @@ GFFT_HD void gfft_strided_cta_phase(int phase, float2 *sm, float2 *data, const f
   } else if (phase <= plan.nfact) {
     int n_cur, s;
     gfft_pass_state(plan, phase - 1, n_cur, s);
-    gfft_pass((phase & 1) ? b0 : b1, (phase & 1) ? b1 : b0, tw, 1, n, W, W, plan.fact[phase - 1], n_cur, s, tid, nthreads);
+    gfft_pass_any(fast, (phase & 1) ? b0 : b1, (phase & 1) ? b1 : b0, tw, 1, n, W, W, plan.fact[phase - 1], n_cur, s, tid, nthreads);
   } else {
     gfft_store_strided((plan.nfact & 1) ? b1 : b0, base, g.stride, n, W, nvalid, tid, nthreads);
   }
@@ -184,7 +260,7 @@ GFFT_HD void gfft_strided_cta_phase(int phase, float2 *sm, float2 *data, const f
 // x axis: plan is the half-length transform (H = n_grid / 2), tw the length-n_grid table (exp(2 pi i j / H) = tw[2 j]),
 // rows of nh = H + 1 modes, W rows per CTA at pitch `pitch` >= W
 GFFT_HD void gfft_rows_cta_phase(int phase, float2 *sm, float2 *data, const float2 *tw, const GfftPlan &plan, int W, int pitch,
-                                 long long nrows, int nh, float norm, long long block, int tid, int nthreads)
+                                 long long nrows, int nh, float norm, int fast, long long block, int tid, int nthreads)
 {
   const int H = plan.n;
   float2 *const b0 = sm, *const b1 = sm + (size_t)H * pitch;
@@ -196,7 +272,7 @@ GFFT_HD void gfft_rows_cta_phase(int phase, float2 *sm, float2 *data, const floa
   } else if (phase <= plan.nfact) {
     int n_cur, s;
     gfft_pass_state(plan, phase - 1, n_cur, s);
-    gfft_pass((phase & 1) ? b0 : b1, (phase & 1) ? b1 : b0, tw, 2, H, W, pitch, plan.fact[phase - 1], n_cur, s, tid, nthreads);
+    gfft_pass_any(fast, (phase & 1) ? b0 : b1, (phase & 1) ? b1 : b0, tw, 2, H, W, pitch, plan.fact[phase - 1], n_cur, s, tid, nthreads);
   } else {
     gfft_rows_gather((plan.nfact & 1) ? b1 : b0, rows, nh, norm, H, W, pitch, nvalid, tid, nthreads);
   }

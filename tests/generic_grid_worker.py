@@ -74,8 +74,18 @@ def main(n, n_side):
         res["run_vs_staged"] = float(np.abs(maps_run[nz] / maps_staged[nz] - 1).max())
         assert res["run_equals_staged_lit"] and res["run_vs_staged"] < TOL, res
         res["kernel_launches"] = int(g.kernel_launches())
-    print("GENERIC_GRID_OK " + json.dumps(res))
+    print("GENERIC_GRID_OK " + json.dumps(res), flush=True)
 
 
 if __name__ == "__main__":
+    if ":" in sys.argv[1]:  # several cases in one process: n_grid:n_side ...
+        bad = 0
+        for spec in sys.argv[1:]:
+            n, ns = (int(v) for v in spec.split(":"))
+            try:
+                main(n, ns)
+            except Exception as exc:  # noqa: BLE001 -- report and go on to the next size
+                bad += 1
+                print(f"GENERIC_GRID_FAILED n_grid={n}: {type(exc).__name__}: {str(exc)[:600]}", flush=True)
+        sys.exit(1 if bad else 0)
     main(int(sys.argv[1]), int(sys.argv[2]))

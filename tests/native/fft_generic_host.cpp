@@ -49,6 +49,8 @@ template <class F> void for_threads(int nthreads, int reverse, F f)
     for (int t = nthreads - 1; t >= 0; --t) f(t);
 }
 
+int g_fast = 0;  // gfft_host_set_fast
+
 int run_strided(float2 *data, const float2 *tw, const GfftPlan &plan, int W, const GfftGeom &g, long long blocks, size_t smem,
                 int nthreads, int reverse)
 {
@@ -56,7 +58,7 @@ int run_strided(float2 *data, const float2 *tw, const GfftPlan &plan, int W, con
   for (long long b = 0; b < blocks; ++b) {
     sm.fill();
     for (int phase = 0; phase < plan.nfact + 2; ++phase)
-      for_threads(nthreads, reverse, [&](int t) { gfft_strided_cta_phase(phase, sm.data(), data, tw, plan, W, g, b, t, nthreads); });
+      for_threads(nthreads, reverse, [&](int t) { gfft_strided_cta_phase(phase, sm.data(), data, tw, plan, W, g, g_fast, b, t, nthreads); });
     if (!sm.intact()) return 1;
   }
   return 0;
@@ -70,13 +72,16 @@ int run_rows(float2 *data, const float2 *tw, const GfftPlan &plan, int W, int pi
     sm.fill();
     for (int phase = 0; phase < plan.nfact + 2; ++phase)
       for_threads(nthreads, reverse,
-                  [&](int t) { gfft_rows_cta_phase(phase, sm.data(), data, tw, plan, W, pitch, nrows, nh, norm, b, t, nthreads); });
+                  [&](int t) { gfft_rows_cta_phase(phase, sm.data(), data, tw, plan, W, pitch, nrows, nh, norm, g_fast, b, t, nthreads); });
     if (!sm.intact()) return 1;
   }
   return 0;
 }
 
 }  // namespace
+
+// 1: one thread per butterfly for the radices 2, 3, 4, 5, 7 (gfft_pass_small); 0: one thread per output element everywhere
+extern "C" void gfft_host_set_fast(int fast) { g_fast = fast; }
 
 // The radix plan of a length (for the tests to inspect): returns nfact, fills fact[16]
 extern "C" int gfft_host_plan(int n, int *fact)

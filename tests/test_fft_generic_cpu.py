@@ -30,6 +30,15 @@ def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
+@pytest.fixture(params=[0, 1], ids=["per_output", "per_butterfly"])
+def fast(lib, request):
+    """0: one thread per output element in every pass (gfft_pass); 1: one thread per butterfly for the radices 2, 3, 4, 5, 7
+    (gfft_pass_small), the rest as before."""
+    lib.gfft_host_set_fast(request.param)
+    yield request.param
+    lib.gfft_host_set_fast(0)
+
+
 def plan_of(lib, n):
     f = np.zeros(16, np.int32)
     k = lib.gfft_host_plan(n, _ptr(f))
@@ -73,7 +82,7 @@ def _spectrum(rng, n, hermitian_planes):
 
 @pytest.mark.parametrize("n", [8, 10, 12, 20, 24, 36, 42, 48, 50, 66, 96, 100])
 @pytest.mark.parametrize("hermitian", [True, False])
-def test_whole_cube_against_numpy(lib, n, hermitian):
+def test_whole_cube_against_numpy(lib, fast, n, hermitian):
     """The three launches of fft_field_generic on an n^3 grid = numpy's c2r (which, like FFTW's and like the tuned
     kernels, never reads Im of the kx = 0 and kx = n/2 planes' self-conjugate partners: non-Hermitian input is
     projected the same way), normalisation included."""
@@ -93,7 +102,7 @@ def test_whole_cube_against_numpy(lib, n, hermitian):
 
 
 @pytest.mark.parametrize("nthreads", [32, 96, 256, 1024])
-def test_any_block_size(lib, nthreads):
+def test_any_block_size(lib, fast, nthreads):
     n = 24
     rng = np.random.default_rng(5)
     x = _spectrum(rng, n, False)
@@ -105,7 +114,7 @@ def test_any_block_size(lib, nthreads):
 
 
 @pytest.mark.parametrize("n", [384, 768, 1000, 1536, 2304, 3000, 3072, 4094])
-def test_production_lengths_pass_by_pass(lib, n):
+def test_production_lengths_pass_by_pass(lib, fast, n):
     """Lengths a production grid would use (incl. 4094 = 2 * 23 * 89: large prime radices): one strided pass over a few
     tiles' worth of lines (the last tile ragged) and one x pass over a few tiles' worth of rows, with the tile widths
     the launcher picks for this length."""
@@ -132,3 +141,22 @@ def test_production_lengths_pass_by_pass(lib, n):
     assert lib.gfft_host_rows(_ptr(buf), n, ctypes.c_longlong(nrows), ctypes.c_double(2.5), 256, 0) == 0
     got = buf.reshape(nrows, 2 * nh)[:, :n]
     assert np.abs(got - want).max() / want.std() < 3e-6
+
+
+@pytest.mark.parametrize("n", [18, 30, 42, 50, 70, 90, 98])
+def test_odd_radix_butterflies_equal_the_per_output_passes_bit_for_bit(lib, n):
+    """Radices 3, 5 and 7 do the same products in the same order either way (only 2 and 4 trade table look-ups of -1 and
+    +-i, whose float sines are 1e-16 rather than 0, for exact butterflies).  The x pass of these grids transforms an odd
+    half-length (9 ... 49): any difference between the two variants would be an indexing slip, not rounding."""
+    assert all(r % 2 for r in plan_of(lib, n // 2))
+    rng = np.random.default_rng(n)
+    nrows, nh = 7, n // 2 + 1
+    x = (rng.standard_normal((nrows, nh)) + 1j * rng.standard_normal((nrows, nh))).astype(np.complex64)
+    out = {}
+    for fast in (0, 1):
+        lib.gfft_host_set_fast(fast)
+        buf = np.ascontiguousarray(x).view(np.float32).copy()
+        assert lib.gfft_host_rows(_ptr(buf), n, ctypes.c_longlong(nrows), ctypes.c_double(1.0), 128, 0) == 0
+        out[fast] = buf
+    lib.gfft_host_set_fast(0)
+    assert np.array_equal(out[0].view(np.uint32), out[1].view(np.uint32))
