@@ -11,7 +11,8 @@ for the GPU count:  1 GPU: 512^3, nside 256, 64 shells;  2/4 GPUs: 1024^3, nside
   e2e   : THE HEADLINE: the same through the reference-facing C-ABI with HOST buffers: parameter tables sent from
           host memory and this rank's finished maps copied back into pinned host memory inside the timed region
   roofline     : the dominant kernel timed alone, algorithmic bytes / duration vs measured HBM peak
-  nvlink       : (N > 1) the transposes fused into the FFT z passes: bytes pushed to peers / z-pass time vs 900 GB/s
+  nvlink       : (N > 1) the FFT transposes (copy-engine peer copies by default): bytes shipped to peers / duration of the
+                 transposition phase vs 900 GB/s
   parity       : (N > 1) a 128^3 slab-decomposed run against the same run on one GPU, done before timing
   strong_scaling : the 1024^3 / nside 512 / 150 shells problem timed at this N (fixed problem for the 1-2-4-8 curve)
   cpu_baseline : the reference's own CPU code (oracle/_ref) on the host cores (N = 1: the same 512^3 configuration)
@@ -432,7 +433,8 @@ def main():
     top = max(cand, key=cand.get)
     peak, peak_src = measured_peaks()
     achieved = bytes_per_cell[top] * nz_cells / (cand[top] * 1e-3) / 1e9
-    kernel_names = {"kgen": "kgen_kernel", "fft": "fft_strided_kernel x4 + fft_c2r_rows_kernel x2", "vel": "radial_velocity_kernel",
+    fft_strided = "fft_strided_tma_kernel" if (n_grid <= 512 and not os.environ.get("GH_FFT_NO_TMA")) or os.environ.get("GH_FFT_TMA") else "fft_strided_kernel"
+    kernel_names = {"kgen": "kgen_kernel", "fft": f"{fft_strided} x4 + fft_c2r_rows_kernel x2", "vel": "radial_velocity_kernel",
                     "sigma": "sigma_partial_kernel", "get_HI": "get_HI_kernel", "maps": "accumulate_kernel"}
     traffic = None
     tf = ROOT / "profiles" / "roofline_traffic.json"

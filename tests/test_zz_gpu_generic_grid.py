@@ -17,16 +17,17 @@ ROOT = Path(__file__).resolve().parents[1]
 
 
 # 48 = 4^2 3, 80 = 4^2 5, 96 = 4^2 2 3: whole 16-cell bricks of the map kernel; 40 = 4 2 5 and 56 = 4 2 7 end in a partial brick;
-# 44 = 4 11: a radix without a butterfly of its own (one thread per output element)
+# 44 = 4 11: a radix without a butterfly of its own (one thread per output element); 384 = 4^3 2 3: a production-sized grid
 @pytest.mark.parametrize("n_grid,n_side,variant", [(48, 16, "butterfly"), (80, 32, "butterfly"), (96, 32, "butterfly"), (40, 16, "butterfly"),
-                                                   (56, 16, "butterfly"), (44, 16, "butterfly"), (48, 16, "per_output"), (40, 16, "per_output")])
+                                                   (56, 16, "butterfly"), (44, 16, "butterfly"), (48, 16, "per_output"), (40, 16, "per_output"),
+                                                   (384, 128, "butterfly")])
 def test_non_power_of_two_grid_against_oracle(n_grid, n_side, variant):
     cmd = [sys.executable, str(ROOT / "tests" / "generic_grid_worker.py"), str(n_grid), str(n_side)]
     env = dict(os.environ)
     env.pop("GH_FFT_GENERIC_SLOW", None)
     if variant == "per_output":
         env["GH_FFT_GENERIC_SLOW"] = "1"
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     out = ROOT / "gpurun_out" / "generic_grid"
     out.mkdir(parents=True, exist_ok=True)
     (out / f"n{n_grid}_{variant}.log").write_text(r.stdout[-4000:] + "\n--- stderr ---\n" + r.stderr[-4000:])
