@@ -37,7 +37,9 @@ extern "C" {
  * pointers are HOST pointers to small tables filled by read_run_params -> cosmo_set
  * (src/io_gh.c:188-296, src/cosmo.c:341-413); they are copied to the device by gh_cuda_create. */
 typedef struct gh_cuda_params {
-  /* grid and geometry (src/cosmo.c:361-364) */
+  /* grid and geometry (src/cosmo.c:361-364).  n_grid: even, 8..4096; powers of two 32..4096 run the tuned FFT kernels and may be
+   * split over a power-of-two number of ranks, other even sizes run general-length passes on one rank (the reference: any
+   * size FFTW takes, src/fourier.c:85) */
   int n_grid;
   double l_box;
   double pos_obs[3];
