@@ -1,4 +1,5 @@
-"""A few seconds on a GPU box, no torch / pytest: (a) the FITS maps of a real ./GetHI run read back through the compiled
+"""Test infrastructure (it uses oracle/_ref as the checker, so it lives under tests/).  A few seconds on a GPU box, no torch /
+pytest: (a) the FITS maps of a real ./GetHI run read back through the compiled
 reference's he_read_healpix_map, (b) the general-length FFT passes against numpy at 192^3 and their time at 384^3 / 768^3
 next to the tuned 512^3 kernels.  Every result is printed (flushed) as soon as it exists."""
 import ctypes as C
